@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- RRI sweeps/sec + achieved HBM GB/s on BASELINE.json's headline configuration
+(dense 200k x 20k low-rank-plus-noise, k=64, fp32, row-sharded over N GPUs of one box).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one full sweep (k T-steps and k W-steps) over the whole data set.  Prints ONE JSON line.
+See DESIGN.md "Measurement" for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: n, d, k (= planted rank), noise, dtype            (BASELINE.json "configs")
+    'cfg1': dict(n=500, d=300, k=10, sigma=0.0, dtype='f64'),
+    'cfg2': dict(n=20000, d=5000, k=32, sigma=0.05, dtype='f64'),
+    'cfg3': dict(n=200000, d=20000, k=64, sigma=0.05, dtype='f32'),
+    'cfg5': dict(n=1000000, d=20000, k=128, sigma=0.05, dtype='f32'),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
+    ap.add_argument('--order', default='hals', choices=['hals', 'rri'])
+    ap.add_argument('--math', default=None, choices=['ieee', 'tf32'])
+    ap.add_argument('--rows', type=int, default=None, help='override n (debugging; the line then says so)')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-rows', type=int, default=None)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        try:
+            j = json.load(open(p))
+            return float(j['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def gen_shard(torch, cfg, rows, row0, device, seed):
+    """X = U V + sigma*mean(UV)*E, uniform factors, generated on the device in row
+    chunks; the shard's rows are rows [row0, row0+rows) of the global matrix in distribution only."""
+    d, r = cfg['d'], cfg['k']
+    dt = torch.float32 if cfg['dtype'] == 'f32' else torch.float64
+    g = torch.Generator(device=device)
+    g.manual_seed(4242)
+    V = torch.rand(r, d, generator=g, device=device, dtype=dt)          # shared by all shards
+    g.manual_seed(1000 + seed)
+    X = torch.empty(rows, d, device=device, dtype=dt)
+    mean_uv = 0.25 * r                                                    # E[u v] * r for U[0,1) factors
+    step = 8192
+    for b in range(0, rows, step):
+        e = min(rows, b + step)
+        U = torch.rand(e - b, r, generator=g, device=device, dtype=dt)
+        torch.matmul(U, V, out=X[b:e])
+        if cfg['sigma']:
+            X[b:e].add_(torch.rand(e - b, d, generator=g, device=device, dtype=dt), alpha=cfg['sigma'] * mean_uv)
+    W0 = torch.rand(rows, cfg['k'], generator=g, device=device, dtype=dt)
+    g.manual_seed(77)
+    T0 = torch.rand(cfg['k'], d, generator=g, device=device, dtype=dt)   # replicated
+    return X, W0, T0
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sweeps(cfg, rows, sweeps, warm=1):
+    """Time the oracle port of the reference's sweep (per-topic GEMVs over X, nmf.py:415-476, interleaved
+    order) on the host cores, on a row sample of the configuration; cost is exactly linear in n, so the
+    full-size figure is the sample's rate scaled by rows/n."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import rri_oracle as orc
+    try:
+        from threadpoolctl import threadpool_info
+        info = [i for i in threadpool_info() if i.get('user_api') == 'blas']
+        blas = '%s %s, %d threads' % (info[0].get('internal_api'), info[0].get('version'), info[0].get('num_threads')) if info else 'unknown BLAS'
+        threads = info[0].get('num_threads') if info else len(os.sched_getaffinity(0))
+    except Exception:
+        blas, threads = 'unknown BLAS', len(os.sched_getaffinity(0))
+    dt = np.float32 if cfg['dtype'] == 'f32' else np.float64
+    X, W0, T0 = orc.synth(rows, cfg['d'], cfg['k'], cfg['k'], sigma=cfg['sigma'], seed=0, dtype=dt)
+    W, T = np.maximum(W0, 0), np.maximum(T0, 0)
+    for _ in range(warm):
+        orc.sweep(X, W, T, order='rri')
+    t0 = time.perf_counter()
+    for _ in range(sweeps):
+        orc.sweep(X, W, T, order='rri')
+    dtm = (time.perf_counter() - t0) / sweeps
+    full = dtm * cfg['n'] / rows
+    return {'value': 1.0 / full, 'unit': 'sweeps/s', 'cores': int(threads), 'kind': 'port',
+            'sample': '%d of %d rows (all %d columns, k=%d, %s), %d sweeps of the interleaved reference order '
+                      '(2k GEMV passes, nmf.py:415-476) timed after %d warm-up, %.3f s/sweep on the sample, scaled '
+                      'linearly in n; %s; host cores available %d'
+                      % (rows, cfg['n'], cfg['d'], cfg['k'], cfg['dtype'], sweeps, warm, dtm, blas,
+                         len(os.sched_getaffinity(0))),
+            'ms_per_sweep_sample': dtm * 1e3}
+
+
+def main_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cfg = dict(CONFIGS[args.config])
+    if args.rows:
+        cfg['n'] = args.rows
+    rows = args.cpu_rows or min(cfg['n'], max(256, cfg['n'] // 40))
+    cb = cpu_reference_sweeps(cfg, rows, sweeps=max(1, args.steps), warm=max(0, min(args.warmup, 1)))
+    line = {
+        'impl': 'reference', 'metric': 'RRI sweeps/sec', 'value': cb['value'], 'unit': 'sweeps/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': cfg['dtype'], 'data': 'synthetic',
+        'config': {'workload': '%s: dense %dx%d low-rank-plus-noise, k=%d, %s' % (args.config, cfg['n'], cfg['d'], cfg['k'], cfg['dtype']),
+                   'update_order': 'rri (the reference has only the interleaved order)', 'sample_rows': rows},
+        'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': 'sweeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rri_nmf_b200 as R
+    from rri_nmf_b200.engine import NcclComm
+    from rri_nmf_b200.sharding import shard_bounds
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('--gpus %d needs torch.distributed.run --nproc-per-node %d' % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    comm = None
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+        comm = NcclComm(local)
+
+    cfg = dict(CONFIGS[args.config])
+    if args.rows:
+        cfg['n'] = args.rows
+    math = args.math or ('tf32' if (cfg['dtype'] == 'f32' and args.order == 'hals') else 'ieee')
+    n, d, k = cfg['n'], cfg['d'], cfg['k']
+    es = 4 if cfg['dtype'] == 'f32' else 8
+    b, e = shard_bounds(n, world)[rank]
+    X, W0, T0 = gen_shard(torch, cfg, e - b, b, device, seed=rank)
+    eng = R.RRIEngine(X, k, order=args.order, math=math, comm=comm)
+    params = eng.params()
+    W, T = W0.clone(), T0.clone()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.sweeps(W, T, 1, params, want_flags=False)
+    barrier()
+    l0 = eng.stats()['kernel_launches']
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.sweeps(W, T, 1, params, want_flags=False)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.stats()['kernel_launches'] - l0
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = 1e3 / ms_per_step
+    relerr = eng.rel_error(W, T)
+
+    # ---- roofline of the dominant kernel (timed alone, CUDA events on the launching stream)
+    peak, peak_src = load_peaks()
+    passes = 2 if args.order == 'hals' else k
+    if args.order == 'hals':
+        kms = 0.5 * (eng.profile_kernel('gemm_w', W, T, 5) + eng.profile_kernel('gemm_t', W, T, 5))
+        kname = 'tf32 tcgen05 contraction (X T\' and X\' W)' if math == 'tf32' else 'simt contraction'
+    else:
+        kms = eng.profile_kernel('rri_pass', W, T, 5)
+        kname = 'rri_pass_kernel (y = X T_t\', p = w_t\' X)'
+    alg_bytes = float(e - b) * d * es                       # one read of the local X per launch
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src, 'kernel_ms': kms,
+                'algorithmic_bytes_per_launch': alg_bytes, 'launches_per_sweep': passes,
+                'sweep_effective_gbs': passes * alg_bytes / (ms_per_step * 1e-3) / 1e9,
+                'kernel_share_of_step': passes * kms / ms_per_step}
+
+    # ---- e2e: the public call with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        try:
+            Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
+            Xh.copy_(X)
+            Wh, Th = W0.cpu().pin_memory(), T0.cpu().pin_memory()
+            del eng
+            torch.cuda.synchronize()
+            s_e2e = args.steps
+            barrier()
+            t0 = time.perf_counter()
+            out = R.nmf(Xh.numpy(), k, W_in=Wh.numpy(), T_in=Th.numpy(), max_iter=s_e2e, reset_topic_method=None,
+                        max_time=1e9, update_order=args.order, math=math, device=device, comm=comm)
+            _ = float(out['W'][0, 0])
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([dt], device=device, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            hb = (Xh.numel() + Wh.numel() + Th.numel()) * es * world
+            db = (Wh.numel() + Th.numel()) * es * world
+            e2e = {'value': s_e2e / dt, 'unit': 'sweeps/s', 'h2d_bytes_per_step': hb / s_e2e,
+                   'd2h_bytes_per_step': db / s_e2e,
+                   'what': 'rri_nmf_b200.nmf(X_host, k, W_in, T_in, max_iter=%d) from pinned host arrays: H2D of X/W/T, '
+                           '%d sweeps, D2H of W/T; %.3f s total' % (s_e2e, s_e2e, dt)}
+        except Exception as ex:        # host RAM too small for a pinned copy, etc.
+            e2e = {'value': None, 'unit': 'sweeps/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None,
+                   'error': repr(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rows = args.cpu_rows or min(n, max(256, n // 40))
+        cpu = cpu_reference_sweeps(cfg, rows, sweeps=2, warm=1)
+
+    if rank == 0:
+        line = {
+            'metric': 'RRI sweeps/sec', 'value': value, 'unit': 'sweeps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': cfg['dtype'] + ('/tf32-mma' if math == 'tf32' else ''), 'data': 'synthetic',
+            'config': {'workload': '%s: dense %dx%d low-rank-plus-noise (sigma=%.2f), k=%d, %s, row-sharded over %d GPU(s)'
+                                   % (args.config, n, d, cfg['sigma'], k, cfg['dtype'], world),
+                       'update_order': args.order, 'math': math, 'rows_per_gpu': e - b,
+                       'l2_policy': 'inputs (%.1f GB/GPU) larger than L2; no flush needed' % (alg_bytes / 1e9),
+                       'final_rel_error': relerr},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        if comm is not None:
+            comm.destroy()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    a = parse()
+    sys.exit(main_reference(a) if a.impl == 'reference' else main_ours(a))

@@ -1,0 +1,810 @@
+// api.cu -- C-ABI (include/rri_b200.h) and sweep orchestration of the B200-native RRI engine.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rri_b200.h"
+#include "gemm_tf32_sm100.h"
+#include "kernels.h"
+
+using namespace rri;
+
+// -------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+#define CK(call)                                                                                \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+
+extern "C" const char* rri_last_error(void) { return g_err; }
+extern "C" const char* rri_version(void) { return "rri_b200 0.1 (sm_100a; tcgen05 tf32 + simt f32/f64)"; }
+
+// -------------------------------------------------------------------------------------------------
+// NCCL through dlsym (no link-time dependency: the library must load on a CPU-only host)
+// -------------------------------------------------------------------------------------------------
+struct Id128 { char b[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load(const char* path)
+{
+    if (g_nccl.lib) return 0;
+    void* lib = nullptr;
+    if (path && *path) lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail("cannot load NCCL (%s): %s", path ? path : "libnccl.so.2", dlerror());
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.AllReduce || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy)
+        return fail("NCCL symbols missing in %s", path ? path : "libnccl.so.2");
+    g_nccl.lib = lib;
+    return 0;
+}
+#define NCK(call)                                                                                \
+    do {                                                                                         \
+        int r_ = (call);                                                                         \
+        if (r_ != 0)                                                                             \
+            return fail("%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+
+extern "C" int rri_nccl_unique_id(char id_out[128], const char* nccl_lib_path)
+{
+    if (nccl_load(nccl_lib_path)) return 1;
+    NCK(g_nccl.GetUniqueId(id_out));
+    return 0;
+}
+extern "C" int rri_nccl_comm_create(void** comm_out, const char id[128], int32_t rank, int32_t world,
+                                    int32_t device, const char* nccl_lib_path)
+{
+    if (nccl_load(nccl_lib_path)) return 1;
+    CK(cudaSetDevice(device));
+    Id128 u;
+    memcpy(u.b, id, 128);
+    NCK(g_nccl.CommInitRank(comm_out, world, u, rank));
+    return 0;
+}
+extern "C" int rri_nccl_comm_destroy(void* comm)
+{
+    if (!g_nccl.lib) return fail("NCCL not loaded");
+    NCK(g_nccl.CommDestroy(comm));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// handle
+// -------------------------------------------------------------------------------------------------
+struct rri_handle_s {
+    int64_t n = 0, d = 0;
+    int k = 0, dtype = 0, math = 0, order = 0, device = 0, sm_count = 148;
+    size_t es = 4;
+    // data
+    const void* X = nullptr; int64_t ldx = 0;
+    const void* M = nullptr; int mk = 0; int64_t ldm = 0;
+    // comm
+    void* comm = nullptr; int rank = 0, world = 1;
+    // workspace
+    std::vector<void*> allocs;
+    int64_t ws_bytes = 0, launches = 0;
+    // rri order
+    PassPlan pp{};
+    int hb = 0, gbw = 0;
+    void *ypart = nullptr, *ppart = nullptr, *gpart = nullptr, *hpart = nullptr, *stat = nullptr;
+    // hals order
+    void *Xt = nullptr; int64_t ldxt = 0;
+    void *Wt = nullptr, *Tt = nullptr, *Cpart = nullptr, *cg = nullptr /* [max(n,d)*k | k*k] */, *Hm = nullptr;
+    void *gram_part = nullptr, *colsum_part = nullptr;
+    int splits_t = 1, splits_w = 1, ub_blocks_t = 1, ub_blocks_w = 1, gchunks_w = 1, gchunks_t = 1;
+    Tf32Gemm* tf32 = nullptr;
+    bool fixT_cached = false;
+    // masked
+    TilePlan tpl{}, wpl{};
+    void *numer_part = nullptr, *denom_part = nullptr, *mstat = nullptr;
+    // common
+    double* sums = nullptr;    // [2k] device
+    int* flags = nullptr;      // device
+    double *obj_part = nullptr, *obj_out = nullptr;
+    int oblocks = 1;
+};
+
+static int ws_alloc(rri_handle_t h, void** p, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    CK(cudaMalloc(p, bytes));
+    CK(cudaMemset(*p, 0, bytes));
+    h->allocs.push_back(*p);
+    h->ws_bytes += (int64_t)bytes;
+    return 0;
+}
+
+extern "C" int rri_create(rri_handle_t* out, int64_t n_local, int64_t d, int32_t k, int32_t dtype,
+                          int32_t math, int32_t order, int32_t device)
+{
+    if (!out) return fail("null handle pointer");
+    if (n_local <= 0 || d <= 0) return fail("n_local and d must be positive (got %lld, %lld)", (long long)n_local, (long long)d);
+    if (k <= 0 || k > 256) return fail("k must be in [1,256] (got %d)", k);
+    if (dtype != RRI_F32 && dtype != RRI_F64) return fail("bad dtype %d", dtype);
+    if (order != RRI_ORDER_RRI && order != RRI_ORDER_HALS) return fail("bad order %d", order);
+    if (math != RRI_MATH_IEEE && math != RRI_MATH_TF32) return fail("bad math %d", math);
+    if (math == RRI_MATH_TF32 && dtype != RRI_F32) return fail("TF32 math needs f32 data");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("bad device %d", device);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail("device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+    rri_handle_t h = new rri_handle_s();
+    h->n = n_local; h->d = d; h->k = k; h->dtype = dtype; h->math = math; h->order = order;
+    h->device = device; h->sm_count = prop.multiProcessorCount;
+    h->es = dtype == RRI_F32 ? 4 : 8;
+    if (ws_alloc(h, (void**)&h->sums, sizeof(double) * 2 * k) || ws_alloc(h, (void**)&h->flags, sizeof(int) * 4)) {
+        rri_destroy(h);
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int rri_destroy(rri_handle_t h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->tf32) tf32_gemm_destroy(h->tf32);
+    delete h;
+    return 0;
+}
+
+extern "C" int rri_set_comm(rri_handle_t h, void* nccl_comm, int32_t rank, int32_t world, const char* nccl_lib_path)
+{
+    if (!h) return fail("null handle");
+    if (world > 1) {
+        if (!nccl_comm) return fail("world > 1 needs a communicator");
+        if (nccl_load(nccl_lib_path)) return 1;
+    }
+    h->comm = nccl_comm; h->rank = rank; h->world = world;
+    return 0;
+}
+
+static int allreduce(rri_handle_t h, void* buf, size_t count, cudaStream_t st)
+{
+    if (h->world <= 1) return 0;
+    NCK(g_nccl.AllReduce(buf, buf, count, h->dtype == RRI_F32 ? 7 : 8, /*ncclSum*/ 0, h->comm, st));
+    h->launches++;
+    return 0;
+}
+
+template <typename T>
+static int bind_impl(rri_handle_t h, cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d;
+    const int k = h->k, ks = k + 1;
+    const size_t es = sizeof(T);
+    h->oblocks = obj_blocks(n, d, h->sm_count);
+    if (!h->obj_part) {
+        if (ws_alloc(h, (void**)&h->obj_part, sizeof(double) * 2 * (size_t)(h->oblocks > 256 ? h->oblocks : 256))) return 1;
+        if (ws_alloc(h, (void**)&h->obj_out, sizeof(double) * 8)) return 1;
+    }
+    if (h->mk != MK_NONE) {
+        if (!h->numer_part) {
+            h->tpl = plan_tstats(n, d, h->sm_count);
+            h->wpl = plan_wstats(n, d, h->sm_count);
+            const size_t a = (size_t)h->tpl.groups * d, b = (size_t)h->wpl.groups * n;
+            const size_t m = a > b ? a : b;
+            if (ws_alloc(h, &h->numer_part, es * m) || ws_alloc(h, &h->denom_part, es * m)) return 1;
+            if (ws_alloc(h, &h->mstat, es * 2 * (size_t)d)) return 1;
+        }
+        return 0;
+    }
+    // the W-only half-step (fix_T, i.e. transform()) always goes through the contraction path
+    if (!h->Cpart) {
+        h->splits_w = simt_gemm_splits(n, d, h->sm_count);
+        h->splits_t = simt_gemm_splits(d, n, h->sm_count);
+        if (h->math == RRI_MATH_TF32) { h->splits_w = 1; h->splits_t = 1; }
+        const size_t a = (size_t)h->splits_w * n * k, b = (size_t)h->splits_t * d * k;
+        if (ws_alloc(h, &h->Cpart, es * (a > b ? a : b))) return 1;
+        const int64_t m = n > d ? n : d;
+        if (ws_alloc(h, &h->cg, es * ((size_t)m * k + (size_t)k * k))) return 1;
+        if (ws_alloc(h, &h->Hm, es * (size_t)k * k)) return 1;
+        if (ws_alloc(h, &h->Wt, es * (size_t)k * n) || ws_alloc(h, &h->Tt, es * (size_t)d * k)) return 1;
+        h->gchunks_w = gram_chunks(n, k, h->sm_count);
+        h->gchunks_t = gram_chunks(d, k, h->sm_count);
+        const int gc = h->gchunks_w > h->gchunks_t ? h->gchunks_w : h->gchunks_t;
+        if (ws_alloc(h, &h->gram_part, es * (size_t)gc * k * k)) return 1;
+        h->ub_blocks_w = update_rows_blocks(n, h->sm_count);
+        h->ub_blocks_t = update_rows_blocks(d, h->sm_count);
+        const int ubm = h->ub_blocks_w > h->ub_blocks_t ? h->ub_blocks_w : h->ub_blocks_t;
+        if (ws_alloc(h, &h->colsum_part, es * (size_t)ubm * k)) return 1;
+        if (h->math == RRI_MATH_TF32) {
+            std::string err;
+            h->tf32 = tf32_gemm_create(h->sm_count, k, err);
+            if (!h->tf32) return fail("tf32 contraction unavailable: %s", err.c_str());
+        }
+    }
+    if (h->order == RRI_ORDER_HALS) {
+        // transposed copy of the data for the T half-step (X' W): both contractions then read
+        // K-contiguous operands
+        const int64_t v = 16 / (int64_t)es;
+        h->ldxt = (n + v - 1) / v * v;
+        if (!h->Xt) { if (ws_alloc(h, &h->Xt, es * (size_t)d * h->ldxt)) return 1; }
+        launch_transpose<T>((const T*)h->X, n, d, h->ldx, (T*)h->Xt, h->ldxt, st);
+        h->launches++;
+        CKL();
+    } else {
+        h->pp = plan_pass(n, d, h->ldx, h->X, (int)es, h->sm_count);
+        h->hb = tstep_blocks(d);
+        h->gbw = wstep_blocks(n, h->sm_count);
+        if (!h->ypart) {
+            if (ws_alloc(h, &h->ypart, es * (size_t)h->pp.ct * n)) return 1;
+            if (ws_alloc(h, &h->ppart, es * (size_t)h->pp.rg * d)) return 1;
+            if (ws_alloc(h, &h->gpart, es * (size_t)h->gbw * ks)) return 1;
+            if (ws_alloc(h, &h->hpart, es * (size_t)h->hb * ks)) return 1;
+            if (ws_alloc(h, &h->stat, es * (size_t)(d + ks))) return 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX, const void* mask_dev,
+                        int32_t mask_kind, int64_t ldM, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!X_dev) return fail("X is null");
+    if (ldX < h->d) return fail("ldX (%lld) < d (%lld)", (long long)ldX, (long long)h->d);
+    if (mask_kind != RRI_MASK_NONE && !mask_dev) return fail("mask kind %d without a mask pointer", mask_kind);
+    if (mask_kind != RRI_MASK_NONE && ldM < h->d) return fail("ldM < d");
+    if (mask_kind < 0 || mask_kind > 2) return fail("bad mask kind %d", mask_kind);
+    if (h->X && ((h->mk != MK_NONE) != (mask_kind != RRI_MASK_NONE)))
+        return fail("a handle cannot switch between masked and unmasked data; create a new one");
+    CK(cudaSetDevice(h->device));
+    h->X = X_dev; h->ldx = ldX;
+    h->M = mask_kind == RRI_MASK_NONE ? nullptr : mask_dev;
+    h->mk = mask_kind; h->ldm = ldM;
+    h->fixT_cached = false;
+    cudaStream_t st = (cudaStream_t)stream;
+    return h->dtype == RRI_F32 ? bind_impl<float>(h, st) : bind_impl<double>(h, st);
+}
+
+static SolveArgs solve_args(const rri_params_t* p, bool forT)
+{
+    SolveArgs a;
+    a.reg_l1 = forT ? p->reg_t_l1 : p->reg_w_l1;
+    a.reg_l2 = forT ? p->reg_t_l2 : p->reg_w_l2;
+    a.eps = p->eps;
+    const double ub = forT ? p->ub_t : p->ub_w;
+    a.has_ub = ub > 0 ? 1 : 0;
+    a.ub = ub > 0 ? ub : 0.0;
+    return a;
+}
+
+static int check_params(rri_handle_t h, const rri_params_t* p)
+{
+    if (!p) return fail("null params");
+    if (!h->X) return fail("rri_bind has not been called");
+    if (p->fix_W && p->fix_T) return fail("fix_W and fix_T both set: nothing to update");
+    if (p->fix_W) return fail("fix_W=True is not supported on the device path (the reference's T-only sweep also rescales W, nmf.py:450-452)");
+    if (p->simplex_T) {
+        if (h->mk != MK_NONE) return fail("project_T_each_iter is not supported together with W_mat on the device path");
+        if (h->order != RRI_ORDER_RRI) return fail("project_T_each_iter couples the columns of T: it needs update_order='rri'");
+        if (!(p->ub_t > 0)) return fail("simplex_T needs t_row_sum > 0");
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// rri order, unmasked
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+static int rri_prologue(rri_handle_t h, T* W, int t0, const rri_params_t* p, cudaStream_t st)
+{
+    // p = w_t0' X and g = w_t0' W for the first T-step (nmf.py:672-673)
+    launch_rri_pass<T>((const T*)h->X, h->ldx, h->n, h->d, nullptr, W, h->k, t0, (T*)h->ypart, (T*)h->ppart,
+                       false, true, h->pp, st);
+    launch_rri_wstep<T>(W, h->n, h->k, 0, t0, (const T*)h->ypart, h->pp.ct, h->n, (const T*)h->hpart, h->hb,
+                        solve_args(p, false), (T*)h->gpart, h->sums, h->flags, false, h->gbw, st);
+    h->launches += 2;
+    CKL();
+    return 0;
+}
+
+template <typename T>
+static int rri_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, bool first_has_prev,
+                           const rri_params_t* p, cudaStream_t st)
+{
+    const int k = h->k;
+    const int64_t n = h->n, d = h->d;
+    const SolveArgs at = solve_args(p, true), aw = solve_args(p, false);
+    for (int t = t0; t < t1; ++t) {
+        const int tn = (t + 1) % k;
+        const int t_prev = (t == t0 && !first_has_prev) ? -1 : (t + k - 1) % k;
+        const T* pp = (const T*)h->ppart; int rg = h->pp.rg;
+        const T* gp = (const T*)h->gpart; int gb = h->gbw;
+        if (h->world > 1) {
+            launch_reduce_stat<T>(pp, rg, d, gp, gb, k, (T*)h->stat, st);
+            h->launches++;
+            if (allreduce(h, h->stat, (size_t)(d + k + 1), st)) return 1;
+            pp = (const T*)h->stat; rg = 1;
+            gp = (const T*)h->stat + d; gb = 1;
+        }
+        launch_rri_tstep<T>(Tm, d, k, t, pp, rg, d, gp, gb, at, (T*)h->hpart, h->sums, t_prev, h->flags, true, st);
+        if (p->simplex_T) {
+            // qf_min with s = t_row_sum projects the scalar-c solution onto the simplex
+            // (optimization.py:58-59); h = T T_t' must then be taken from the projected row
+            launch_project_rows_simplex<T>(Tm + (int64_t)t * d, 1, d, p->ub_t, st);
+            launch_rri_tstep<T>(Tm, d, k, t, pp, rg, d, gp, gb, at, (T*)h->hpart, h->sums, -1, h->flags, false, st);
+            h->launches += 2;
+        }
+        launch_rri_pass<T>((const T*)h->X, h->ldx, n, d, Tm + (int64_t)t * d, W, k, tn, (T*)h->ypart,
+                           (T*)h->ppart, true, true, h->pp, st);
+        launch_rri_wstep<T>(W, n, k, t, tn, (const T*)h->ypart, h->pp.ct, n, (const T*)h->hpart, h->hb, aw,
+                            (T*)h->gpart, h->sums, h->flags, true, h->gbw, st);
+        h->launches += 3;
+    }
+    CKL();
+    return 0;
+}
+
+template <typename T>
+static int rri_finish(rri_handle_t h, int t_last, cudaStream_t st)
+{
+    // the sum of the last updated W column has no consumer kernel: finalize it here
+    if (h->world > 1) {
+        launch_reduce_stat<T>((const T*)h->ppart, 0, 0, (const T*)h->gpart, h->gbw, h->k, (T*)h->stat, st);
+        if (allreduce(h, h->stat, (size_t)(h->k + 1), st)) return 1;
+        launch_finalize_sums<T>((const T*)h->stat, 1, h->k, t_last, h->sums, h->flags, st);
+        h->launches += 2;
+    } else {
+        launch_finalize_sums<T>((const T*)h->gpart, h->gbw, h->k, t_last, h->sums, h->flags, st);
+        h->launches++;
+    }
+    CKL();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// hals order, unmasked
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+static int contraction(rri_handle_t h, const T* A, int64_t lda, const T* B, int64_t ldb, T* Cpart,
+                       int64_t M, int N, int64_t K, int splits, cudaStream_t st)
+{
+    if (h->math == RRI_MATH_TF32) {
+        std::string err;
+        int nl = tf32_gemm_run(h->tf32, (const float*)A, lda, (const float*)B, ldb, (float*)Cpart, N, M, N, K, st, err);
+        if (nl < 0) return fail("tf32 contraction failed: %s", err.c_str());
+        h->launches += nl;
+    } else {
+        launch_simt_gemm_nt<T>(A, lda, B, ldb, Cpart, M, N, K, splits, st);
+        h->launches++;
+    }
+    return 0;
+}
+
+template <typename T>
+static int hals_W_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, bool recompute, cudaStream_t st)
+{
+    const int k = h->k;
+    const int64_t n = h->n, d = h->d;
+    if (recompute) {
+        // H = T T' from the d x k transposed copy, C2 = X T'
+        launch_gram<T>((const T*)h->Tt, d, k, (T*)h->gram_part, h->gchunks_t, (T*)h->Hm, st);
+        h->launches += 2;
+        if (contraction<T>(h, (const T*)h->X, h->ldx, Tm, d, (T*)h->Cpart, n, k, d, h->splits_w, st)) return 1;
+    }
+    const int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_w;
+    launch_update_rows<T>(W, n, k, (const T*)h->Cpart, parts, n * k, (const T*)h->Hm, solve_args(p, false),
+                          (T*)h->Wt, (T*)h->colsum_part, h->flags, h->ub_blocks_w, st);
+    launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_w, k, h->sums, k, h->world > 1 ? 0 : 2, h->flags, st);
+    h->launches += 2;
+    if (h->world > 1) {
+        // the zero-column test of nmf.py:793 is over ALL rows: all-reduce the shard sums (doubles)
+        NCK(g_nccl.AllReduce(h->sums + k, h->sums + k, (size_t)k, 8, 0, h->comm, st));
+        launch_flag_from_sums(h->sums, k, k, 2, h->flags, st);
+        h->launches += 2;
+    }
+    CKL();
+    return 0;
+}
+
+template <typename T>
+static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaStream_t st)
+{
+    const int k = h->k;
+    const int64_t n = h->n, d = h->d;
+    T* cg = (T*)h->cg;                 // [d*k | k*k]: X'W partial followed by W'W partial, all-reduced together
+    T* G = cg + (size_t)d * k;
+    launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, G, st);
+    h->launches += 2;
+    if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, n, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
+    const T* C = (const T*)h->Cpart;
+    int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_t;
+    if (h->world > 1) {
+        launch_reduce_parts<T>(C, parts, d * k, d * k, cg, st);
+        h->launches++;
+        if (allreduce(h, cg, (size_t)d * k + (size_t)k * k, st)) return 1;
+        C = cg; parts = 1;
+    }
+    // Tt (d x k) is updated in place; its transpose is written straight into the caller's T (k x d)
+    launch_update_rows<T>((T*)h->Tt, d, k, C, parts, d * k, G, solve_args(p, true), Tm, (T*)h->colsum_part,
+                          h->flags, h->ub_blocks_t, st);
+    launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_t, k, h->sums, 0, 1, h->flags, st);
+    h->launches += 2;
+    CKL();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// masked WRRI (both orders)
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+static int wrri_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d;
+    launch_wrri_tstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, n, d, h->k, t, (T*)h->numer_part,
+                          (T*)h->denom_part, h->tpl, st);
+    h->launches++;
+    const T* nu = (const T*)h->numer_part; const T* de = (const T*)h->denom_part;
+    int parts = h->tpl.groups;
+    if (h->world > 1) {
+        T* ms = (T*)h->mstat;
+        launch_reduce_parts<T>(nu, parts, d, d, ms, st);
+        launch_reduce_parts<T>(de, parts, d, d, ms + d, st);
+        h->launches += 2;
+        if (allreduce(h, ms, (size_t)2 * d, st)) return 1;
+        nu = ms; de = ms + d; parts = 1;
+    }
+    launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), Tm + (int64_t)t * d, 1, h->flags, st);
+    launch_vec_sum_flag<T>(Tm + (int64_t)t * d, d, 1, h->sums, t, 1, h->flags, st);
+    h->launches += 2;
+    return 0;
+}
+
+template <typename T>
+static int wrri_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d;
+    launch_wrri_wstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, n, d, h->k, t, (T*)h->numer_part,
+                          (T*)h->denom_part, h->wpl, st);
+    launch_wrri_final<T>((const T*)h->numer_part, (const T*)h->denom_part, h->wpl.groups, n, solve_args(p, false),
+                         W + t, h->k, h->flags, st);
+    launch_vec_sum_flag<T>(W + t, n, h->k, h->sums, h->k + t, h->world > 1 ? 0 : 2, h->flags, st);
+    h->launches += 3;
+    if (h->world > 1) {
+        // the zero-column test of nmf.py:793 is over ALL rows: all-reduce the shard sum (a double)
+        NCK(g_nccl.AllReduce(h->sums + h->k + t, h->sums + h->k + t, 1, 8, 0, h->comm, st));
+        launch_flag_from_sums(h->sums, h->k + t, 1, 2, h->flags, st);
+        h->launches += 2;
+    }
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// sweeps
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_params_t* p, cudaStream_t st)
+{
+    const int k = h->k;
+    const int64_t n = h->n, d = h->d;
+    if (h->mk != MK_NONE) {
+        for (int s = 0; s < n_sweeps; ++s) {
+            if (h->order == RRI_ORDER_RRI) {
+                for (int t = 0; t < k; ++t) {
+                    if (!p->fix_T && wrri_T_step<T>(h, W, Tm, t, p, st)) return 1;
+                    if (!p->fix_W && wrri_W_step<T>(h, W, Tm, t, p, st)) return 1;
+                }
+            } else {
+                if (!p->fix_T) for (int t = 0; t < k; ++t) if (wrri_T_step<T>(h, W, Tm, t, p, st)) return 1;
+                if (!p->fix_W) for (int t = 0; t < k; ++t) if (wrri_W_step<T>(h, W, Tm, t, p, st)) return 1;
+            }
+        }
+        CKL();
+        return 0;
+    }
+    if (p->fix_T) {
+        // W-only sweeps (transform(): sklearn_interface.py:327-334): X T' and T T' are constant, so
+        // one pass over X serves every sweep; both update orders coincide here
+        launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
+        h->launches++;
+        for (int s = 0; s < n_sweeps; ++s)
+            if (hals_W_half<T>(h, W, Tm, p, s == 0, st)) return 1;
+        return 0;
+    }
+    if (h->order == RRI_ORDER_HALS) {
+        launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
+        launch_transpose<T>(W, n, k, k, (T*)h->Wt, n, st);
+        h->launches += 2;
+        for (int s = 0; s < n_sweeps; ++s) {
+            if (hals_T_half<T>(h, W, Tm, p, st)) return 1;
+            if (hals_W_half<T>(h, W, Tm, p, true, st)) return 1;
+        }
+        return 0;
+    }
+    if (rri_prologue<T>(h, W, 0, p, st)) return 1;
+    for (int s = 0; s < n_sweeps; ++s)
+        if (rri_topic_range<T>(h, W, Tm, 0, k, s > 0, p, st)) return 1;
+    return rri_finish<T>(h, k - 1, st);
+}
+
+static int read_flags(rri_handle_t h, int32_t* flags_host, cudaStream_t st)
+{
+    if (!flags_host) return 0;
+    CK(cudaMemcpyAsync(flags_host, h->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+extern "C" int rri_sweeps(rri_handle_t h, void* W_dev, void* T_dev, int32_t n_sweeps, const rri_params_t* p,
+                          int32_t* flags_host, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!W_dev || !T_dev) return fail("W or T is null");
+    if (n_sweeps < 0) return fail("n_sweeps < 0");
+    if (check_params(h, p)) return 1;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+    if (n_sweeps > 0) {
+        int rc = h->dtype == RRI_F32 ? sweeps_impl<float>(h, (float*)W_dev, (float*)T_dev, n_sweeps, p, st)
+                                     : sweeps_impl<double>(h, (double*)W_dev, (double*)T_dev, n_sweeps, p, st);
+        if (rc) return rc;
+    }
+    return read_flags(h, flags_host, st);
+}
+
+template <typename T>
+static int topics_impl(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri_params_t* p, cudaStream_t st)
+{
+    if (h->mk != MK_NONE) {
+        for (int t = t0; t < t1; ++t) {
+            if (wrri_T_step<T>(h, W, Tm, t, p, st)) return 1;
+            if (wrri_W_step<T>(h, W, Tm, t, p, st)) return 1;
+        }
+        CKL();
+        return 0;
+    }
+    if (rri_prologue<T>(h, W, t0, p, st)) return 1;
+    if (rri_topic_range<T>(h, W, Tm, t0, t1, false, p, st)) return 1;
+    return rri_finish<T>(h, t1 - 1, st);
+}
+
+extern "C" int rri_topics(rri_handle_t h, void* W_dev, void* T_dev, int32_t t_begin, int32_t t_end,
+                          const rri_params_t* p, int32_t* flags_host, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!W_dev || !T_dev) return fail("W or T is null");
+    if (check_params(h, p)) return 1;
+    if (h->order != RRI_ORDER_RRI) return fail("rri_topics needs a handle created with RRI_ORDER_RRI");
+    if (p->fix_T) return fail("rri_topics does not take fix_T");
+    if (t_begin < 0 || t_end > h->k || t_begin >= t_end) return fail("bad topic range [%d,%d)", t_begin, t_end);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+    int rc = h->dtype == RRI_F32 ? topics_impl<float>(h, (float*)W_dev, (float*)T_dev, t_begin, t_end, p, st)
+                                 : topics_impl<double>(h, (double*)W_dev, (double*)T_dev, t_begin, t_end, p, st);
+    if (rc) return rc;
+    return read_flags(h, flags_host, st);
+}
+
+extern "C" int rri_topic_sums(rri_handle_t h, double* sum_T_host, double* sum_W_host, void* stream)
+{
+    if (!h) return fail("null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    if (sum_T_host) CK(cudaMemcpyAsync(sum_T_host, h->sums, sizeof(double) * h->k, cudaMemcpyDeviceToHost, st));
+    if (sum_W_host) CK(cudaMemcpyAsync(sum_W_host, h->sums + h->k, sizeof(double) * h->k, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// objective, partial statistic, misc
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+static int objective_impl(rri_handle_t h, const T* W, const T* Tm, cudaStream_t st)
+{
+    launch_objective<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, h->n, h->d, h->k, h->obj_part,
+                        h->oblocks, h->obj_out, st);
+    launch_norms<T>(W, h->n * h->k, h->obj_part, h->obj_out + 2, st);
+    launch_norms<T>(Tm, (int64_t)h->k * h->d, h->obj_part, h->obj_out + 4, st);
+    h->launches += 6;
+    CKL();
+    return 0;
+}
+
+extern "C" int rri_objective(rri_handle_t h, const void* W_dev, const void* T_dev, double* out_host, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!h->X) return fail("rri_bind has not been called");
+    if (!W_dev || !T_dev || !out_host) return fail("null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = h->dtype == RRI_F32 ? objective_impl<float>(h, (const float*)W_dev, (const float*)T_dev, st)
+                                 : objective_impl<double>(h, (const double*)W_dev, (const double*)T_dev, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_host, h->obj_out, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+template <typename T>
+__global__ void partials_unmasked_kernel(const T* __restrict__ stat, const T* __restrict__ Tm, int64_t d, int k,
+                                         int t, T* __restrict__ wR, T* __restrict__ nw)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < d) {
+        T dot = T(0);
+        for (int j = 0; j < k; ++j)
+            if (j != t) dot = fma(stat[d + j], Tm[(int64_t)j * d + c], dot);     // nmf.py:674-675
+        wR[c] = stat[c] - dot;
+    }
+    if (c == 0) nw[0] = stat[d + t];                                                // nmf.py:676
+}
+
+template <typename T>
+static int partials_impl(rri_handle_t h, const T* W, const T* Tm, int t, T* wR, T* nw, cudaStream_t st)
+{
+    const int64_t d = h->d;
+    rri_params_t p;
+    memset(&p, 0, sizeof(p));
+    if (h->mk != MK_NONE) {
+        launch_wrri_tstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, h->n, d, h->k, t,
+                              (T*)h->numer_part, (T*)h->denom_part, h->tpl, st);
+        launch_reduce_parts<T>((const T*)h->numer_part, h->tpl.groups, d, d, wR, st);
+        launch_reduce_parts<T>((const T*)h->denom_part, h->tpl.groups, d, d, nw, st);
+        h->launches += 3;
+    } else {
+        if (h->order != RRI_ORDER_RRI) return fail("rri_partials_T (unmasked) needs a handle created with RRI_ORDER_RRI");
+        if (rri_prologue<T>(h, const_cast<T*>(W), t, &p, st)) return 1;     // prologue does not write W
+        launch_reduce_stat<T>((const T*)h->ppart, h->pp.rg, d, (const T*)h->gpart, h->gbw, h->k, (T*)h->stat, st);
+        partials_unmasked_kernel<T><<<(unsigned)((d + 255) / 256), 256, 0, st>>>((const T*)h->stat, Tm, d, h->k, t, wR, nw);
+        h->launches += 2;
+    }
+    CKL();
+    return 0;
+}
+
+extern "C" int rri_partials_T(rri_handle_t h, const void* W_dev, const void* T_dev, int32_t t, void* out_wR_dev,
+                              void* out_nw_dev, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!h->X) return fail("rri_bind has not been called");
+    if (t < 0 || t >= h->k) return fail("bad topic %d", t);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    return h->dtype == RRI_F32
+               ? partials_impl<float>(h, (const float*)W_dev, (const float*)T_dev, t, (float*)out_wR_dev, (float*)out_nw_dev, st)
+               : partials_impl<double>(h, (const double*)W_dev, (const double*)T_dev, t, (double*)out_wR_dev, (double*)out_nw_dev, st);
+}
+
+extern "C" int rri_project_rows_simplex(rri_handle_t h, void* A_dev, int64_t rows, int64_t cols, double s, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!A_dev || rows <= 0 || cols <= 0) return fail("bad matrix");
+    if (!(s > 0)) return fail("Radius s must be strictly positive");          // matrixops.py:42
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->dtype == RRI_F32) launch_project_rows_simplex<float>((float*)A_dev, rows, cols, s, st);
+    else launch_project_rows_simplex<double>((double*)A_dev, rows, cols, s, st);
+    h->launches++;
+    CKL();
+    return 0;
+}
+
+extern "C" int rri_stats(rri_handle_t h, int64_t* kernel_launches, int64_t* workspace_bytes)
+{
+    if (!h) return fail("null handle");
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (workspace_bytes) *workspace_bytes = h->ws_bytes;
+    return 0;
+}
+
+extern "C" int rri_gemm_nt(rri_handle_t h, const void* A_dev, int64_t lda, const void* B_dev, int64_t ldb,
+                           void* C_dev, int64_t ldc, int64_t M, int32_t N, int64_t K, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (N <= 0 || N > 256 || M <= 0 || K <= 0) return fail("bad shape");
+    if (ldc != N) return fail("ldc must equal N");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->math == RRI_MATH_TF32) {
+        if (!h->tf32) {
+            std::string err;
+            h->tf32 = tf32_gemm_create(h->sm_count, N > h->k ? N : h->k, err);
+            if (!h->tf32) return fail("tf32 contraction unavailable: %s", err.c_str());
+        }
+        std::string err;
+        int nl = tf32_gemm_run(h->tf32, (const float*)A_dev, lda, (const float*)B_dev, ldb, (float*)C_dev, N, M, N, K, st, err);
+        if (nl < 0) return fail("tf32 contraction failed: %s", err.c_str());
+        h->launches += nl;
+    } else if (h->dtype == RRI_F32) {
+        launch_simt_gemm_nt<float>((const float*)A_dev, lda, (const float*)B_dev, ldb, (float*)C_dev, M, N, K, 1, st);
+        h->launches++;
+    } else {
+        launch_simt_gemm_nt<double>((const double*)A_dev, lda, (const double*)B_dev, ldb, (double*)C_dev, M, N, K, 1, st);
+        h->launches++;
+    }
+    CKL();
+    return 0;
+}
+
+template <typename T>
+static int profile_impl(rri_handle_t h, int which, const T* W, const T* Tm, int iters, float* avg_ms, cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d;
+    const int k = h->k;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    if (which == 2 && h->mk == MK_NONE && h->order == RRI_ORDER_HALS) {
+        launch_transpose<T>(W, n, k, k, (T*)h->Wt, n, st);
+        h->launches++;
+    }
+    for (int it = -1; it < iters; ++it) {          // one untimed warm-up launch
+        if (it == 0) CK(cudaEventRecord(e0, st));
+        if (which == 0) {
+            if (h->mk != MK_NONE || h->order != RRI_ORDER_RRI) return fail("which=0 needs an unmasked rri-order handle");
+            launch_rri_pass<T>((const T*)h->X, h->ldx, n, d, Tm, W, k, 1 % k, (T*)h->ypart, (T*)h->ppart, true, true, h->pp, st);
+            h->launches++;
+        } else if (which == 1) {
+            if (h->mk != MK_NONE) return fail("which=1 needs an unmasked handle");
+            if (contraction<T>(h, (const T*)h->X, h->ldx, Tm, d, (T*)h->Cpart, n, k, d, h->splits_w, st)) return 1;
+        } else if (which == 2) {
+            if (h->mk != MK_NONE || h->order != RRI_ORDER_HALS) return fail("which=2 needs an unmasked hals-order handle");
+            if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, n, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
+        } else {
+            return fail("bad kernel selector %d", which);
+        }
+    }
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaEventDestroy(e0));
+    CK(cudaEventDestroy(e1));
+    CKL();
+    *avg_ms = ms / (float)iters;
+    return 0;
+}
+
+extern "C" int rri_profile_kernel(rri_handle_t h, int32_t which, const void* W_dev, const void* T_dev, int32_t iters,
+                                  float* avg_ms_host, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!h->X) return fail("rri_bind has not been called");
+    if (!W_dev || !T_dev || !avg_ms_host || iters <= 0) return fail("bad argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    return h->dtype == RRI_F32 ? profile_impl<float>(h, which, (const float*)W_dev, (const float*)T_dev, iters, avg_ms_host, st)
+                               : profile_impl<double>(h, which, (const double*)W_dev, (const double*)T_dev, iters, avg_ms_host, st);
+}

@@ -1,0 +1,433 @@
+// hals_kernels.cu -- block-order (HALS) half-steps, unmasked.
+//
+// With the other factor frozen, the k rank-one updates of one factor only need
+//     C = A B'   (one streaming contraction over the data: X T' for W, X' W for T)
+//     S = B B'   (k x k Gram)
+// and then every row of the factor is updated independently by k sequential scalar solves --
+// the arithmetic of nmf.py:670-676 + :437-447 (T) / :728-734 + :464-469 (W), reordered so that X
+// is read twice per sweep instead of 2k times (BASELINE.json north_star groups (1)+(2)).
+// This file holds the IEEE (fp32/fp64 SIMT) contraction, the row-update kernel and the Gram
+// kernel; the TF32 tcgen05 contraction lives in gemm_tf32_sm100.cu.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rri {
+
+// ------------------------------------------------------------------------------------------------
+// SIMT contraction C = A B^T   (A: M x K, B: N x K, both K-contiguous)
+// ------------------------------------------------------------------------------------------------
+constexpr int G_BM = 64, G_BK = 16, G_THREADS = 256;
+
+template <typename T, int KT>
+__global__ void __launch_bounds__(G_THREADS)
+simt_gemm_nt_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb,
+                    T* __restrict__ Cpart, int64_t M, int N, int64_t K)
+{
+    constexpr int BN = 16 * KT;
+    __shared__ T As[G_BK][G_BM + 4];
+    __shared__ T Bs[G_BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * G_BM;
+    int64_t k0, k1;
+    part_range((K + G_BK - 1) / G_BK, gridDim.y, blockIdx.y, k0, k1);
+    k0 *= G_BK; k1 = (k1 * G_BK < K) ? k1 * G_BK : K;
+
+    T acc[4][KT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < KT; ++j) acc[i][j] = T(0);
+
+    const int arow = tid >> 2, akk = (tid & 3) * 4;
+    for (int64_t kb = k0; kb < k1; kb += G_BK) {
+        {   // A tile: 64 rows x 16
+            const int64_t gm = m0 + arow;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t gk = kb + akk + e;
+                As[akk + e][arow] = (gm < M && gk < k1) ? ld_stream(A + gm * lda + gk) : T(0);
+            }
+        }
+        for (int e = tid; e < BN * G_BK; e += G_THREADS) {
+            const int row = e / G_BK, kk = e % G_BK;
+            const int64_t gk = kb + kk;
+            Bs[kk][row] = (row < N && gk < k1) ? B[(int64_t)row * ldb + gk] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < G_BK; ++kk) {
+            T a[4], b[KT];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < KT; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < KT; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    T* C = Cpart + (int64_t)blockIdx.y * M * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t gm = m0 + ty * 4 + i;
+        if (gm < M) {
+#pragma unroll
+            for (int j = 0; j < KT; ++j) {
+                const int gn = tx + 16 * j;
+                if (gn < N) C[gm * N + gn] = acc[i][j];
+            }
+        }
+    }
+}
+
+int simt_gemm_splits(int64_t M, int64_t K, int sm_count)
+{
+    const int64_t tiles = (M + G_BM - 1) / G_BM;
+    int64_t s = (2 * sm_count + tiles - 1) / tiles;
+    const int64_t maxs = (K + 8 * G_BK - 1) / (8 * G_BK);        // >= 128 k-elements per slice
+    if (s > maxs) s = maxs;
+    if (s > 64) s = 64;
+    return (int)(s < 1 ? 1 : s);
+}
+
+template <typename T>
+void launch_simt_gemm_nt(const T* A, int64_t lda, const T* B, int64_t ldb, T* Cpart, int64_t M, int N,
+                         int64_t K, int splits, cudaStream_t st)
+{
+    dim3 grid((unsigned)((M + G_BM - 1) / G_BM), splits);
+    const int kt = (N + 15) / 16;
+#define RRI_G_CASE(KT) simt_gemm_nt_kernel<T, KT><<<grid, G_THREADS, 0, st>>>(A, lda, B, ldb, Cpart, M, N, K)
+    if (kt <= 1) RRI_G_CASE(1);
+    else if (kt <= 2) RRI_G_CASE(2);
+    else if (kt <= 4) RRI_G_CASE(4);
+    else if (kt <= 8) RRI_G_CASE(8);
+    else RRI_G_CASE(16);
+#undef RRI_G_CASE
+}
+
+// ------------------------------------------------------------------------------------------------
+// row update: warp per row, lanes own coordinates t' = lane + 32 l
+// ------------------------------------------------------------------------------------------------
+constexpr int U_THREADS = 256, U_NW = U_THREADS / WARP, U_GROUP = 32;   // rows per block iteration
+
+int update_rows_blocks(int64_t m, int sm_count)
+{
+    int64_t b = (m + U_GROUP - 1) / U_GROUP;
+    if (b > 4 * sm_count) b = 4 * sm_count;
+    return (int)(b < 1 ? 1 : b);
+}
+
+template <typename T, int KL, bool S_SMEM>
+__global__ void __launch_bounds__(U_THREADS)
+update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cpart, int parts,
+                   int64_t part_stride, const T* __restrict__ S,
+                   T reg_l1, T reg_l2, T eps, T ub, int has_ub,
+                   T* __restrict__ Ft, T* __restrict__ colsum_part, int* __restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* ftile = reinterpret_cast<T*>(smem_raw);                 // [k][U_GROUP+1]
+    T* csm = ftile + (size_t)k * (U_GROUP + 1);                // [U_NW][k]
+    T* Ss = csm + (size_t)U_NW * k;                            // [k][k] when S_SMEM
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (S_SMEM) {
+        for (int e = tid; e < k * k; e += U_THREADS) Ss[e] = S[e];
+        __syncthreads();
+    }
+    const T* Sp = S_SMEM ? Ss : S;
+
+    T csum[KL];
+#pragma unroll
+    for (int l = 0; l < KL; ++l) csum[l] = T(0);
+    bool unb = false;
+
+    const int64_t ngroups = (m + U_GROUP - 1) / U_GROUP;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t i0 = g * U_GROUP;
+#pragma unroll 1
+        for (int q = 0; q < U_GROUP / U_NW; ++q) {
+            const int ii = warp + U_NW * q;
+            const int64_t i = i0 + ii;
+            if (i < m) {
+                T f[KL], r[KL];
+#pragma unroll
+                for (int l = 0; l < KL; ++l) {
+                    const int tp = lane + 32 * l;
+                    f[l] = T(0); r[l] = T(0);
+                    if (tp < k) {
+                        f[l] = F[i * k + tp];
+                        T c = T(0);
+                        for (int p = 0; p < parts; ++p) c += Cpart[(int64_t)p * part_stride + i * k + tp];
+                        r[l] = c;
+                    }
+                }
+                // r[t'] = C[i,t'] - sum_{j != t'} F[i,j] S[j,t']
+#pragma unroll
+                for (int l0 = 0; l0 < KL; ++l0) {
+                    for (int tt = 0; tt < 32; ++tt) {
+                        const int j = 32 * l0 + tt;
+                        if (j >= k) break;
+                        const T fj = __shfl_sync(0xffffffffu, f[l0], tt);
+#pragma unroll
+                        for (int l = 0; l < KL; ++l) {
+                            const int tp = lane + 32 * l;
+                            if (tp < k && tp != j) r[l] = fma(-fj, Sp[j * k + tp], r[l]);
+                        }
+                    }
+                }
+                // sequential solves; after topic t changes by delta, r[t'] -= delta * S[t,t']
+#pragma unroll
+                for (int l0 = 0; l0 < KL; ++l0) {
+                    for (int tt = 0; tt < 32; ++tt) {
+                        const int t = 32 * l0 + tt;
+                        if (t >= k) break;
+                        T delta = T(0);
+                        if (lane == tt) {
+                            const T x = solve_scalar_c<T>(r[l0] - reg_l1, Sp[t * k + t] + reg_l2, eps, ub,
+                                                          has_ub != 0, unb);
+                            delta = x - f[l0];
+                            f[l0] = x;
+                        }
+                        delta = __shfl_sync(0xffffffffu, delta, tt);
+#pragma unroll
+                        for (int l = 0; l < KL; ++l) {
+                            const int tp = lane + 32 * l;
+                            if (tp < k && tp != t) r[l] = fma(-delta, Sp[t * k + tp], r[l]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int l = 0; l < KL; ++l) {
+                    const int tp = lane + 32 * l;
+                    if (tp < k) {
+                        F[i * k + tp] = f[l];
+                        csum[l] += f[l];
+                        if (Ft) ftile[tp * (U_GROUP + 1) + ii] = f[l];
+                    }
+                }
+            }
+        }
+        if (Ft) {
+            __syncthreads();
+            for (int e = tid; e < k * U_GROUP; e += U_THREADS) {
+                const int tp = e / U_GROUP, ii = e % U_GROUP;
+                if (i0 + ii < m) Ft[(int64_t)tp * m + i0 + ii] = ftile[tp * (U_GROUP + 1) + ii];
+            }
+            __syncthreads();
+        }
+    }
+    if (unb) atomicOr(flags, 4);
+#pragma unroll
+    for (int l = 0; l < KL; ++l) {
+        const int tp = lane + 32 * l;
+        if (tp < k) csm[warp * k + tp] = csum[l];
+    }
+    __syncthreads();
+    for (int tp = tid; tp < k; tp += U_THREADS) {
+        T s = T(0);
+#pragma unroll
+        for (int w = 0; w < U_NW; ++w) s += csm[w * k + tp];
+        colsum_part[(int64_t)blockIdx.x * k + tp] = s;
+    }
+}
+
+template <typename T, int KL>
+static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
+                                  const T* S, const SolveArgs& a, T* Ft, T* colsum_part, int* flags,
+                                  int blocks, cudaStream_t st)
+{
+    size_t base = sizeof(T) * ((size_t)k * (U_GROUP + 1) + (size_t)U_NW * k);
+    size_t with_s = base + sizeof(T) * (size_t)k * k;
+    if (with_s <= 200 * 1024) {
+        auto kern = update_rows_kernel<T, KL, true>;
+        if (with_s > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_s);
+        kern<<<blocks, U_THREADS, with_s, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1,
+                                                 (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft,
+                                                 colsum_part, flags);
+    } else {
+        auto kern = update_rows_kernel<T, KL, false>;
+        if (base > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
+        kern<<<blocks, U_THREADS, base, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1,
+                                               (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft,
+                                               colsum_part, flags);
+    }
+}
+
+template <typename T>
+void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
+                        const T* S, const SolveArgs& a, T* Ft, T* colsum_part, int* flags, int blocks,
+                        cudaStream_t st)
+{
+    const int kl = (k + 31) / 32;
+    if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
+    else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
+    else if (kl <= 4) launch_update_rows_kl<T, 4>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
+    else launch_update_rows_kl<T, 8>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gram G = F'F
+// ------------------------------------------------------------------------------------------------
+constexpr int GR_ROWS = 32;      // rows staged per iteration
+
+int gram_chunks(int64_t m, int k, int sm_count)
+{
+    const int kb = (k + 63) / 64;
+    int64_t c = (2 * sm_count) / (kb * kb);
+    const int64_t maxc = (m + 4 * GR_ROWS - 1) / (4 * GR_ROWS);
+    if (c > maxc) c = maxc;
+    return (int)(c < 1 ? 1 : c);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gram_kernel(const T* __restrict__ F, int64_t m, int k, T* __restrict__ part)
+{
+    __shared__ T Fa[GR_ROWS][64 + 1];
+    __shared__ T Fb[GR_ROWS][64 + 1];
+    const int kb = (k + 63) / 64;
+    const int a0 = (blockIdx.y / kb) * 64, b0 = (blockIdx.y % kb) * 64;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    int64_t r0, r1;
+    part_range(m, gridDim.x, blockIdx.x, r0, r1);
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int64_t rb = r0; rb < r1; rb += GR_ROWS) {
+        for (int e = tid; e < GR_ROWS * 64; e += 256) {
+            const int rr = e / 64, cc = e % 64;
+            const int64_t gr = rb + rr;
+            Fa[rr][cc] = (gr < r1 && a0 + cc < k) ? F[gr * k + a0 + cc] : T(0);
+            Fb[rr][cc] = (gr < r1 && b0 + cc < k) ? F[gr * k + b0 + cc] : T(0);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < GR_ROWS; ++rr) {
+            T a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Fa[rr][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Fb[rr][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    T* P = part + (int64_t)blockIdx.x * k * k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = a0 + ty + 16 * i, b = b0 + tx + 16 * j;
+            if (a < k && b < k) P[a * k + b] = acc[i][j];
+        }
+}
+
+template <typename T>
+__global__ void reduce_parts_kernel(const T* __restrict__ part, int parts, int64_t stride, int64_t len,
+                                    T* __restrict__ out)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < len) {
+        T s = T(0);
+        for (int p = 0; p < parts; ++p) s += part[(int64_t)p * stride + c];
+        out[c] = s;
+    }
+}
+
+template <typename T>
+void launch_reduce_parts(const T* part, int parts, int64_t stride, int64_t len, T* out, cudaStream_t st)
+{
+    reduce_parts_kernel<T><<<(unsigned)((len + 255) / 256), 256, 0, st>>>(part, parts, stride, len, out);
+}
+
+template <typename T>
+void launch_gram(const T* F, int64_t m, int k, T* part, int chunks, T* G, cudaStream_t st)
+{
+    const int kb = (k + 63) / 64;
+    dim3 grid(chunks, kb * kb);
+    gram_kernel<T><<<grid, 256, 0, st>>>(F, m, k, part);
+    launch_reduce_parts<T>(part, chunks, (int64_t)k * k, (int64_t)k * k, G, st);
+}
+
+template <typename T>
+__global__ void colsum_finalize_kernel(const T* __restrict__ colsum_part, int blocks, int k,
+                                       double* __restrict__ sums, int off, int zero_flag,
+                                       int* __restrict__ flags)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < k) {
+        T s = T(0);
+        for (int b = 0; b < blocks; ++b) s += colsum_part[(int64_t)b * k + t];
+        const double v = (double)s;
+        sums[off + t] = v;
+        if (!(v > 1e-10)) atomicOr(flags, zero_flag);
+        if (!isfinite(v)) atomicOr(flags, 8);
+    }
+}
+
+template <typename T>
+void launch_colsum_finalize(const T* colsum_part, int blocks, int k, double* sums, int off,
+                            int zero_flag, int* flags, cudaStream_t st)
+{
+    colsum_finalize_kernel<T><<<(k + 127) / 128, 128, 0, st>>>(colsum_part, blocks, k, sums, off, zero_flag, flags);
+}
+
+// ------------------------------------------------------------------------------------------------
+// transpose
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const T* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, T* __restrict__ B, int64_t ldb)
+{
+    __shared__ T tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int64_t r = r0 + ty + j, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + j][tx] = A[r * lda + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int64_t c = c0 + ty + j, r = r0 + tx;
+        if (r < rows && c < cols) B[c * ldb + r] = tile[tx][ty + j];
+    }
+}
+
+template <typename T>
+void launch_transpose(const T* A, int64_t rows, int64_t cols, int64_t lda, T* B, int64_t ldb, cudaStream_t st)
+{
+    // grid.y is limited to 65535 blocks -> tile rows over x when rows is the long side
+    const int64_t bx = (cols + 31) / 32, by = (rows + 31) / 32;
+    if (by <= 65535) {
+        dim3 grid((unsigned)bx, (unsigned)by);
+        transpose_kernel<T><<<grid, 256, 0, st>>>(A, rows, cols, lda, B, ldb);
+    } else {
+        for (int64_t r = 0; r < rows; r += 65535LL * 32) {
+            const int64_t rr = (rows - r) < 65535LL * 32 ? (rows - r) : 65535LL * 32;
+            dim3 grid((unsigned)bx, (unsigned)((rr + 31) / 32));
+            transpose_kernel<T><<<grid, 256, 0, st>>>(A + r * lda, rr, cols, lda, B + r, ldb);
+        }
+    }
+}
+
+#define RRI_INST(T)                                                                                       \
+    template void launch_simt_gemm_nt<T>(const T*, int64_t, const T*, int64_t, T*, int64_t, int, int64_t, \
+                                         int, cudaStream_t);                                              \
+    template void launch_update_rows<T>(T*, int64_t, int, const T*, int, int64_t, const T*,               \
+                                        const SolveArgs&, T*, T*, int*, int, cudaStream_t);               \
+    template void launch_gram<T>(const T*, int64_t, int, T*, int, T*, cudaStream_t);                      \
+    template void launch_reduce_parts<T>(const T*, int, int64_t, int64_t, T*, cudaStream_t);              \
+    template void launch_colsum_finalize<T>(const T*, int, int, double*, int, int, int*, cudaStream_t);   \
+    template void launch_transpose<T>(const T*, int64_t, int64_t, int64_t, T*, int64_t, cudaStream_t);
+RRI_INST(float)
+RRI_INST(double)
+
+}  // namespace rri

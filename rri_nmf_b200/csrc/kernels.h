@@ -1,0 +1,153 @@
+// kernels.h -- host-side launchers of the sweep kernels (internal; the public ABI is include/rri_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rri {
+
+// ---------------------------------------------------------------------------------------------
+// rri (interleaved) order, unmasked: three kernels per topic        (rri_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+struct PassPlan {
+    int vec;        // elements per 16-byte load (1 when X is not 16-byte tileable)
+    int nch;        // column chunks per thread
+    int ct;         // column tiles  (gridDim.x)
+    int rg;         // row groups    (gridDim.y)
+    int64_t cw;     // columns per tile
+};
+PassPlan plan_pass(int64_t n, int64_t d, int64_t ldx, const void* X, int elem_size, int sm_count);
+
+// y[ct][i] = sum_{c in tile ct} X[i,c]*tvec[c]   and   p[rg][c] = sum_{i in group rg} W[i,tn]*X[i,c]
+template <typename T>
+void launch_rri_pass(const T* X, int64_t ldx, int64_t n, int64_t d, const T* tvec, const T* W, int k,
+                     int tn, T* ypart, T* ppart, bool do_y, bool do_p, const PassPlan& pl,
+                     cudaStream_t st);
+
+struct SolveArgs {      // one half-step's scalar parameters, already in the element type's range
+    double reg_l1, reg_l2, eps, ub;
+    int has_ub;
+};
+
+int tstep_blocks(int64_t d);
+int wstep_blocks(int64_t n, int sm_count);
+
+// T-step of topic t (nmf.py:420-447) + partial h = T T_t' (nmf.py:730) for the following W-step
+template <typename T>
+void launch_rri_tstep(T* Tm, int64_t d, int k, int t, const T* ppart, int rg, int64_t pstride,
+                      const T* gpart, int gb, const SolveArgs& a, T* hpart, double* sums, int t_prev,
+                      int* flags, bool do_update, cudaStream_t st);
+
+// W-step of topic t (nmf.py:462-469) + partial g = w_tn' W (nmf.py:673) for the following T-step
+template <typename T>
+void launch_rri_wstep(T* W, int64_t n, int k, int t, int tn, const T* ypart, int ct, int64_t ystride,
+                      const T* hpart, int hb, const SolveArgs& a, T* gpart, double* sums, int* flags,
+                      bool do_update, int blocks, cudaStream_t st);
+
+// stat[0..d) = sum_rg ppart, stat[d..d+k] = sum_b gpart   (the row-shard statistic, nmf.py:680-686)
+template <typename T>
+void launch_reduce_stat(const T* ppart, int rg, int64_t d, const T* gpart, int gb, int k, T* stat,
+                        cudaStream_t st);
+
+// sums[k + t_prev] = sum over blocks of gpart slot k (sum of the last updated W column) + flags
+template <typename T>
+void launch_finalize_sums(const T* gpart, int gb, int k, int t_prev, double* sums, int* flags,
+                          cudaStream_t st);
+
+}  // namespace rri
+
+namespace rri {
+// ---------------------------------------------------------------------------------------------
+// hals (block) order, unmasked: contraction + row update + Gram          (hals_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+// IEEE SIMT contraction  C[p][M,N] = A[M, Kp] * B[N, Kp]^T  over `splits` K-slices p (deterministic:
+// the consumer adds the slices in order).  N <= 256.
+int simt_gemm_splits(int64_t M, int64_t K, int sm_count);
+template <typename T>
+void launch_simt_gemm_nt(const T* A, int64_t lda, const T* B, int64_t ldb, T* Cpart, int64_t M, int N,
+                         int64_t K, int splits, cudaStream_t st);
+
+// Sequential coordinate update of every row of F[m,k] (block-order HALS half-step):
+//   for t: F[i,t] <- [ C[i,t] - sum_{j!=t} F[i,j] S[j,t] - reg_l1 ]_+ / (S[t,t] + reg_l2 + eps)
+// C = sum of `parts` slices of Cpart.  Writes F in place, optionally Ft[k,m] = F', and per-block
+// column sums colsum_part[blocks][k].   (nmf.py:420-447 / :462-469 applied with the other factor frozen)
+int update_rows_blocks(int64_t m, int sm_count);
+template <typename T>
+void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
+                        const T* S, const SolveArgs& a, T* Ft, T* colsum_part, int* flags, int blocks,
+                        cudaStream_t st);
+
+// Gram matrix G[k,k] = F'F of a row-major F[m,k]: per-chunk partials + fixed-order finalize.
+int gram_chunks(int64_t m, int k, int sm_count);
+template <typename T>
+void launch_gram(const T* F, int64_t m, int k, T* part, int chunks, T* G, cudaStream_t st);
+
+// out[c] = sum_b part[b][c]  (c < len) -- generic fixed-order reduction of per-block partials
+template <typename T>
+void launch_reduce_parts(const T* part, int parts, int64_t stride, int64_t len, T* out, cudaStream_t st);
+
+// sums[off + t] = sum_b colsum_part[b][t]; sets zero-topic / non-finite flags
+template <typename T>
+void launch_colsum_finalize(const T* colsum_part, int blocks, int k, double* sums, int off,
+                            int zero_flag, int* flags, cudaStream_t st);
+
+// B[c, r] = A[r, c]  (A is rows x cols with leading dimension lda; B has leading dimension ldb)
+template <typename T>
+void launch_transpose(const T* A, int64_t rows, int64_t cols, int64_t lda, T* B, int64_t ldb,
+                      cudaStream_t st);
+}  // namespace rri
+
+namespace rri {
+// ---------------------------------------------------------------------------------------------
+// masked / weighted WRRI half-steps and the objective                      (wrri_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+enum { MK_NONE = 0, MK_REAL = 1, MK_U8 = 2 };
+
+struct TilePlan { int tiles_r, tiles_c, groups; };      // groups = partial slices written
+TilePlan plan_tstats(int64_t n, int64_t d, int sm_count);
+TilePlan plan_wstats(int64_t n, int64_t d, int sm_count);
+
+// T-step statistics of topic t over the local rows (nmf.py:687-701):
+//   numer_part[g][c] = sum_{i in group g} W[i,t] * M[i,c] * (X[i,c] - sum_{j!=t} W[i,j] T[j,c])
+//   denom_part[g][c] = sum_{i in group g} W[i,t]^2 * M[i,c]
+template <typename T>
+void launch_wrri_tstats(const T* X, int64_t ldx, const void* M, int mk, int64_t ldm, const T* W,
+                        const T* Tm, int64_t n, int64_t d, int k, int t, T* numer_part, T* denom_part,
+                        const TilePlan& pl, cudaStream_t st);
+// W-step statistics of topic t (nmf.py:735-746): numer_part[g][i], denom_part[g][i] over column groups
+template <typename T>
+void launch_wrri_wstats(const T* X, int64_t ldx, const void* M, int mk, int64_t ldm, const T* W,
+                        const T* Tm, int64_t n, int64_t d, int k, int t, T* numer_part, T* denom_part,
+                        const TilePlan& pl, cudaStream_t st);
+// vector-c solve (optimization.py:75-84) of out[idx*stride] for idx < len from `parts` partial slices
+template <typename T>
+void launch_wrri_final(const T* numer_part, const T* denom_part, int parts, int64_t len,
+                       const SolveArgs& a, T* out, int64_t out_stride, int* flags, cudaStream_t st);
+// sums[slot] = sum_i v[i*stride]; zero/non-finite flags (single block, fixed order)
+template <typename T>
+void launch_vec_sum_flag(const T* v, int64_t len, int64_t stride, double* sums, int slot, int zero_flag,
+                         int* flags, cudaStream_t st);
+// v[i*stride] *= scale / sums[slot]   (vector-c branch with a sum constraint, optimization.py:85-87)
+template <typename T>
+void launch_vec_scale_to_sum(T* v, int64_t len, int64_t stride, const double* sums, int slot, double s,
+                             cudaStream_t st);
+
+// objective pieces over the local rows (nmf.py:71-94): out[0] = 0.5*sum M (X-WT)^2, out[1] = sum M X^2
+int obj_blocks(int64_t n, int64_t d, int sm_count);
+template <typename T>
+void launch_objective(const T* X, int64_t ldx, const void* M, int mk, int64_t ldm, const T* W,
+                      const T* Tm, int64_t n, int64_t d, int k, double* part, int blocks, double* out,
+                      cudaStream_t st);
+// out[0] = sum v^2, out[1] = sum |v| over len contiguous elements (regulariser terms, nmf.py:72-75)
+template <typename T>
+void launch_norms(const T* v, int64_t len, double* part, double* out, cudaStream_t st);
+}  // namespace rri
+
+namespace rri {
+// sets `zero_flag` when any sums[off + t] <= 1e-10 (after a cross-shard all-reduce of the sums)
+void launch_flag_from_sums(const double* sums, int off, int k, int zero_flag, int* flags, cudaStream_t st);
+
+// rows of A[rows, cols] <- Euclidean projection onto {x >= 0, sum x = s}   (simplex_kernels.cu;
+// matrixops.py:5-69 computes the same threshold by sorting)
+template <typename T>
+void launch_project_rows_simplex(T* A, int64_t rows, int64_t cols, double s, cudaStream_t st);
+}  // namespace rri

@@ -1,0 +1,364 @@
+"""`nmf(X, k, **kwargs) -> dict` -- the reference's solver entry point (src/rri_nmf/nmf.py:98-560) with
+its two inner loops (`for iter_no ... for t in range(k)`, :377, :415-476) running on the B200 through
+librri_b200.so.  The outer shell stays Python: argument validation, initialisation, stopping policy,
+early stop, topic reset, return dict -- same names, meaning and error behaviour as the reference.
+
+Additional keyword-only arguments select the device path:
+    device        torch device (default 'cuda'); there is NO CPU fallback
+    update_order  'rri'  -- the reference's interleaved order (default; exact drop-in), or
+                  'hals' -- block order: all T-steps then all W-steps (2 passes over X per sweep)
+    math          'ieee' (default) or 'tf32' (tcgen05 tensor-core contractions; float32 + 'hals')
+    comm          engine.NcclComm for a row-sharded multi-GPU run (X, W_in, W_mat are the local shards)
+"""
+import logging
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._host import initialize_nmf, normalize
+from .engine import RRIEngine, EPS_DIV_BY_ZERO
+
+logger = logging.getLogger(__name__)
+eps_div_by_zero = EPS_DIV_BY_ZERO          # nmf.py:52
+
+
+class DeviceObjective(object):
+    """Stand-in for the reference's TrueObjComputer (nmf.py:58-94) returned as 'obj_calculator'."""
+
+    def __init__(self, engine, W, T, regs):
+        self.engine, self.W, self.T, self.regs = engine, W, T, regs
+        self.obj = np.inf
+
+    def true_objective(self):
+        self.obj = self.engine.objective(self.W, self.T, **self.regs)
+        return self.obj
+
+
+def _universal_stopping_condition(obj_history, eps_stop=1e-4):
+    """optimization.py:284-291"""
+    if len(obj_history) < 2:
+        return False
+    return abs(obj_history[-1] - obj_history[-2]) <= eps_stop * abs(obj_history[0] - obj_history[1])
+
+
+def _is_empty(a):
+    return a is None or int(np.prod(np.shape(a))) == 0
+
+
+def _to_device(a, device, dtype):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype)
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a)
+    if device.type == 'cuda' and t.numel() > (1 << 20):
+        try:
+            t = t.pin_memory()
+        except RuntimeError:
+            pass
+    return t.to(device=device, dtype=dtype, non_blocking=True)
+
+
+def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=None, init='nndsvd', T_in=[],
+        W_in=[], max_iter=200, max_time=600, eps_stop=1e-4, compute_obj_each_iter=False,
+        project_W_each_iter=False, w_row_sum=None, do_final_project_W=True, project_T_each_iter=False,
+        t_row_sum=None, early_stop=None, reset_topic_method='max_resid_document', fix_reset_seed=False,
+        n_resets=23, reg_w_l2=0, reg_t_l2=0, reg_w_l1=0, reg_t_l1=0, diagnostics=[], store_gradients=False,
+        ind_rows_to_store=None, eps_gauss_t=None, delta_gauss_t=None,
+        *, device=None, update_order='rri', math='ieee', comm=None, engine=None, sweeps_per_call=16):
+    """Non-negative factorisation X ~ W T by rank-one residue iteration.  See the reference docstring
+    (nmf.py:109-269) for the arguments; returns {'W', 'T', 'iter_cputime', 'random_state'[, 'obj_history',
+    'obj_calculator', 'diagnostics']} (nmf.py:551-560).  W and T come back as the kind of array X was
+    (NumPy in -> NumPy out, torch tensor in -> torch tensors on the device)."""
+    lib = _lib.load()           # fail loudly before doing anything if the CUDA library is missing
+    del lib
+    if update_order not in ('rri', 'hals'):
+        raise ValueError("update_order must be 'rri' or 'hals'")
+    n, d = X.shape
+    rtv = {}
+    numpy_io = not isinstance(X, torch.Tensor)
+
+    # ---- argument policy, as nmf.py:280-315
+    if project_T_each_iter and np.any([reg_w_l1, reg_t_l1]):
+        logger.warning('This implementation can not solve project_T_each_iter=True with regularization. '
+                       'Setting project_T_each_iter to False.')
+        project_T_each_iter = False
+    if (not project_T_each_iter and not t_row_sum) and (reg_t_l1 < 0 or reg_t_l2 < 0):
+        logger.error('Unbounded objective. reg_t_l1=%s, reg_t_l2=%s', reg_t_l1, reg_t_l2)
+        return {'W': np.ones((n, k)), 'T': np.ones((k, d)) * 1e6, 'obj_history': [-np.inf], 'iter_cputime': [0]}
+    if (not project_W_each_iter and not w_row_sum) and (reg_w_l1 < 0 or reg_w_l2 < 0):
+        logger.error('Unbounded objective. reg_w_l1=%s, reg_w_l2=%s', reg_w_l1, reg_w_l2)
+        return {'W': np.ones((n, k)) * 1e6, 'T': np.ones((k, d)), 'obj_history': [-np.inf], 'iter_cputime': [0]}
+
+    # ---- features of nmf() that are outside the accelerated path fail loudly
+    if w_row is not None:
+        raise NotImplementedError('w_row (row weighting + W-only sub-solve, nmf.py:335-344, :531-539) is not '
+                                  'on the device path; pre-scale X by sqrt(w_row) on the host')
+    if eps_gauss_t or delta_gauss_t:
+        raise NotImplementedError('the Gaussian DP mechanism (nmf.py:422-435) is not on the device path')
+    if store_gradients:
+        raise NotImplementedError('store_gradients: use RRIEngine.partials_T (the statistic of nmf.py:680-686)')
+    if fix_W:
+        raise NotImplementedError('fix_W=True is not on the device path (the reference T-only sweep also '
+                                  'rescales W, nmf.py:450-452)')
+    if w_row_sum is not None and not np.isscalar(w_row_sum):
+        raise NotImplementedError('vector w_row_sum is not on the device path')
+    if type(diagnostics) is not list:
+        diagnostics = [diagnostics]
+    if len(diagnostics) > 0:
+        rtv['diagnostics'] = {f.__name__: [] for f in diagnostics}
+    if random_state is None:
+        random_state = int(time.time()) % 4294967296
+    t_global_start = time.time()
+    max_time = max_time - 10                                     # nmf.py:333
+    if n <= k:
+        init = 'random'                                          # nmf.py:346-347
+    start_time = time.process_time()
+
+    # ---- device placement
+    if device is None:
+        device = X.device if isinstance(X, torch.Tensor) and X.is_cuda else torch.device('cuda')
+    device = torch.device(device)
+    if not torch.cuda.is_available():
+        raise _lib.RriError('no CUDA device is available: rri_nmf_b200.nmf has no CPU fallback')
+    if device.type != 'cuda':
+        raise _lib.RriError('rri_nmf_b200.nmf runs on CUDA devices only (no CPU fallback)')
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    if isinstance(X, torch.Tensor):
+        dtype = X.dtype if X.dtype in (torch.float32, torch.float64) else torch.float64
+    else:
+        dtype = torch.float32 if np.asarray(X).dtype == np.float32 else torch.float64
+
+    # ---- initialisation and validation, as nmf.py:819-880
+    if _is_empty(W_in) or _is_empty(T_in):
+        Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
+        Mh = None
+        if W_mat is not None:
+            Mh = W_mat.detach().cpu().numpy() if isinstance(W_mat, torch.Tensor) else np.asarray(W_mat)
+        W0, T0 = initialize_nmf(Mh * Xh if Mh is not None else Xh, k, init, random_state=random_state,
+                                row_normalize=False)
+        if t_row_sum is not None:
+            T0 = normalize(T0) * t_row_sum
+        if w_row_sum is not None:
+            W0 = normalize(W0) * w_row_sum
+    if not _is_empty(W_in):
+        if tuple(np.shape(W_in)) != (n, k):
+            raise ValueError('W_in has wrong dimensions, must be n*k')
+        W0 = W_in
+    if not _is_empty(T_in):
+        if tuple(np.shape(T_in)) != (k, d):
+            raise ValueError('T_in has wrong dimensions, must be k*d')
+        T0 = T_in
+    with torch.cuda.device(device):
+        Xd = _to_device(X, device, dtype)
+        # np.maximum(W_in, 0) makes copies: the caller's arrays are never mutated (nmf.py:867-868)
+        W = _to_device(W0, device, dtype).clamp(min=0).contiguous()
+        T = _to_device(T0, device, dtype).clamp(min=0).contiguous()
+        if W.data_ptr() == (W0.data_ptr() if isinstance(W0, torch.Tensor) else 0):
+            W = W.clone()
+        if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
+            T = T.clone()
+        Md = None
+        if W_mat is not None:
+            if isinstance(W_mat, torch.Tensor) and W_mat.dtype in (torch.uint8, torch.bool):
+                Md = W_mat.to(device)
+            else:
+                Md = _to_device(W_mat, device, dtype)
+
+        own_engine = engine is None
+        if engine is None:
+            engine = RRIEngine(Xd, k, W_mat=Md, order=update_order, math=math, comm=comm)
+        try:
+            return _solve(engine, Xd, W, T, rtv, locals())
+        finally:
+            if own_engine:
+                engine.close()
+
+
+def _solve(engine, Xd, W, T, rtv, a):
+    """Sweep loop and post-processing: nmf.py:351-560."""
+    k, n, d = a['k'], a['n'], a['d']
+    fix_T = a['fix_T']
+    w_row_sum, t_row_sum = a['w_row_sum'], a['t_row_sum']
+    project_T_each_iter, project_W_each_iter = a['project_T_each_iter'], a['project_W_each_iter']
+    early_stop, diagnostics = a['early_stop'], a['diagnostics']
+    compute_obj_each_iter, eps_stop = a['compute_obj_each_iter'], a['eps_stop']
+    reset_topic_method = a['reset_topic_method']
+    max_iter, max_time, t_global_start = a['max_iter'], a['max_time'], a['t_global_start']
+    numpy_io = a['numpy_io']
+    regs = dict(reg_w_l1=a['reg_w_l1'], reg_w_l2=a['reg_w_l2'], reg_t_l1=a['reg_t_l1'], reg_t_l2=a['reg_t_l2'])
+
+    if project_W_each_iter and not a['fix_W'] and w_row_sum is not None:          # nmf.py:870-873
+        engine.project_rows_simplex(W, w_row_sum)
+    if project_T_each_iter and not fix_T and t_row_sum is not None:               # nmf.py:875-878
+        engine.project_rows_simplex(T, t_row_sum)
+
+    params = engine.params(ub_w=w_row_sum, ub_t=t_row_sum, fix_T=fix_T,
+                           simplex_T=bool(project_T_each_iter and t_row_sum and not fix_T), **regs)
+    masked = engine.W_mat is not None
+
+    def host_view(t):
+        return t.detach().cpu().numpy() if numpy_io else t
+
+    Xcb = host_view(Xd) if (callable(early_stop) or diagnostics) else None
+    state = {'n_resets_remaining': a['n_resets']}
+    iter_cputime = []
+    obj_history = []
+    OBJ = DeviceObjective(engine, W, T, regs) if compute_obj_each_iter else None
+    if early_stop:
+        last_score = np.inf
+        W_prev, T_prev = W.clone(), T.clone()
+    for f in diagnostics:
+        rtv['diagnostics'][f.__name__].append(f(Xcb, host_view(W), host_view(T)))
+
+    # sweeps can be batched into one library call when nothing on the host has to look at the state
+    # in between (N sweeps in one call == N calls of one sweep, bit for bit)
+    per_sweep_host = bool(early_stop) or compute_obj_each_iter or bool(diagnostics) or \
+        (project_W_each_iter and w_row_sum is not None) or reset_topic_method is not None
+    chunk = 1 if per_sweep_host else max(1, int(a['sweeps_per_call']))
+    can_reset = reset_topic_method is not None and engine.order == 'rri' and not masked
+
+    iter_no = 0
+    while iter_no < max_iter:
+        if early_stop:                                                             # nmf.py:381-407
+            if callable(early_stop):
+                this_score = early_stop(Xcb, host_view(W), host_view(T))
+            else:
+                this_score = obj_history[-1] if (compute_obj_each_iter and obj_history) else np.inf
+            if this_score > last_score:
+                W.copy_(W_prev)
+                T.copy_(T_prev)
+                obj_history = obj_history[:-1]
+                iter_cputime = iter_cputime[:-1]
+                for f in diagnostics:
+                    rtv['diagnostics'][f.__name__] = rtv['diagnostics'][f.__name__][:-1]
+                break
+            last_score = this_score
+            W_prev.copy_(W)
+            T_prev.copy_(T)
+        ns = min(chunk, max_iter - iter_no)
+        if can_reset:
+            W_save, T_save = W.clone(), T.clone()
+        flags = engine.sweeps(W, T, ns, params, want_flags=True)
+        if flags & (_lib.FLAG_ZERO_T | _lib.FLAG_ZERO_W) and can_reset and state['n_resets_remaining'] > 0:
+            # rare path: redo this sweep topic by topic with the reset policy of nmf.py:762-783, :796-816
+            W.copy_(W_save)
+            T.copy_(T_save)
+            flags = _sweep_with_resets(engine, Xd, W, T, params, a, state)
+        _raise_on_flags(flags, engine)
+        iter_no += ns
+        if project_W_each_iter and not a['fix_W'] and w_row_sum is not None:      # nmf.py:481-484
+            engine.project_rows_simplex(W, w_row_sum)
+        if compute_obj_each_iter:                                                  # nmf.py:488-489
+            obj_history.append(OBJ.true_objective())
+        now = time.process_time()
+        iter_cputime.extend([now] * ns)
+        for f in diagnostics:                                                      # nmf.py:495-500
+            rtv['diagnostics'][f.__name__].append(f(Xcb, host_view(W), host_view(T)))
+        if time.time() - t_global_start >= max_time:                               # nmf.py:506-508
+            break
+        if compute_obj_each_iter and _universal_stopping_condition(obj_history, eps_stop):   # :510-514
+            break
+    iter_cputime = [x - a['start_time'] for x in iter_cputime]
+
+    if (not project_W_each_iter and w_row_sum is not None and not a['fix_W'] and a['do_final_project_W']):
+        engine.project_rows_simplex(W, w_row_sum)                                  # nmf.py:519-529
+
+    torch.cuda.current_stream(W.device).synchronize()
+    rtv['W'] = host_view(W)
+    rtv['T'] = host_view(T)
+    if compute_obj_each_iter:
+        rtv['obj_history'] = obj_history
+        rtv['obj_calculator'] = OBJ
+    rtv['iter_cputime'] = iter_cputime
+    rtv['random_state'] = a['random_state']
+    return rtv
+
+
+def _raise_on_flags(flags, engine):
+    if flags & _lib.FLAG_UNBOUNDED:
+        # optimization.py:60-67 / :76-77 -> _unbounded_objective (:105-107)
+        raise ValueError('Minimum objective is unbounded. (a denominator became <= 0 with no upper bound; '
+                         'typically a topic collapsed to zero while reset_topic_method is None)')
+    if flags & _lib.FLAG_NONFINITE:
+        raise FloatingPointError('non-finite values produced in the sweep')
+    if flags & _lib.FLAG_ZERO_W:
+        if np.any(engine.topic_sums()[1] <= 0):
+            raise AssertionError('W[:, t] sums to 0')                              # nmf.py:476
+
+
+def _sweep_with_resets(engine, Xd, W, T, params, a, state):
+    """One rri-order sweep executed topic by topic so that an emptied topic can be re-seeded exactly
+    where the reference does it (nmf.py:458 -> :762-783 after the T-step, :471 -> :796-816 after the
+    W-step).  The device runs the topic; the reset itself (a full residual, rare) uses torch ops."""
+    k = engine.k
+    flags_all = 0
+    method = a['reset_topic_method']
+
+    def reset(t):
+        if state['n_resets_remaining'] == 0:
+            return
+        state['n_resets_remaining'] -= 1
+        if method == 'max_resid_document':
+            R = (Xd - W @ T).clamp_(min=0)
+            mi = int(torch.argmax((R ** 2).sum(1)))
+            T[t, :] = R[mi, :]
+            W[:, t] = 0
+            W[mi, t] = 1.0
+        elif method == 'random':
+            if a['fix_reset_seed']:
+                np.random.seed(t + int(torch.argmax(T[t, :])))
+            r = np.random.rand(1, engine.d)
+            T[t, :] = torch.from_numpy(r / r.sum()).to(T)
+            W[:, t] = torch.from_numpy(np.random.rand(engine.n)).to(W)
+        else:
+            raise ValueError('unknown reset_topic_method %r' % (method,))
+
+    t = 0
+    while t < k:
+        W_save, T_save = W.clone(), T.clone()
+        f = engine.topics(W, T, t, t + 1, params)
+        sT, sW = engine.topic_sums()
+        if f & _lib.FLAG_ZERO_T and sT[t] <= 1e-10 and state['n_resets_remaining'] > 0:
+            # the reference resets right after the T-step, then runs the W-step on the re-seeded topic
+            W.copy_(W_save)
+            T.copy_(T_save)
+            _t_step_only(engine, W, T, t, params)
+            reset(t)
+            _w_step_only(engine, W, T, t, params)
+            sT, sW = engine.topic_sums()
+            f &= ~_lib.FLAG_ZERO_T
+        if sW[t] <= 1e-10 and state['n_resets_remaining'] > 0:
+            reset(t)
+            f &= ~_lib.FLAG_ZERO_W
+        flags_all |= f
+        t += 1
+    return flags_all
+
+
+def _t_step_only(engine, W, T, t, params):
+    """T-step of topic t alone: run the topic on copies and keep only the new T row."""
+    W2, T2 = W.clone(), T.clone()
+    engine.topics(W2, T2, t, t + 1, params)
+    T[t, :] = T2[t, :]
+
+
+def _w_step_only(engine, W, T, t, params):
+    """W-step of topic t with T frozen: a fix_T sweep restricted to column t is a single row-local
+    solve; with T fixed, columns j != t are inputs only, so run fix_T topics on a copy and keep column t.
+    (nmf.py:462-469 with the current T.)"""
+    import copy
+    p2 = copy.copy(params)
+    # W-only step for one topic == the reference W-step: numer = X T_t' - W (T T_t')_{t->0}
+    Tt = T[t, :]
+    h = T @ Tt
+    nt = float(h[t])
+    h[t] = 0
+    numer = engine.X @ Tt - W @ h - params.reg_w_l1
+    denom = nt + params.reg_w_l2
+    if denom > 0:
+        W[:, t] = numer.clamp(min=0) / (denom + params.eps)
+    else:
+        W[:, t] = 0
