@@ -31,7 +31,7 @@ CONFIGS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
@@ -57,7 +57,9 @@ def load_peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the poller runs from program
+    start (nvidia-smi takes a while to come up); `window()` keeps the samples whose host arrival time
+    falls inside the timed region (or the nearest one when the region is shorter than a poll period)."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -70,7 +72,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -78,19 +80,26 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def window(self, t0, t1):
+        if self.proc is None or not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.06]
+        if not inside:
+            mid = 0.5 * (t0 + t1)
+            inside = [min(self.rows, key=lambda tr: abs(tr[0] - mid))[1]]
+        sm, mx, pw, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith('active'):
                         reasons.add(nm)
@@ -98,7 +107,7 @@ class ClockSampler(object):
                 pass
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'power_w_max': max(pw) if pw else None, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
 def gen_shard(torch, cfg, rows, row0, device, seed):
@@ -221,22 +230,28 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         eng.sweeps(W, T, 1, params, want_flags=False)
     barrier()
     l0 = eng.stats()['kernel_launches']
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    th0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         eng.sweeps(W, T, 1, params, want_flags=False)
     ev1.record()
     barrier()
+    th1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        time.sleep(0.12)
+        clocks = sampler.window(th0, th1)
+        sampler.stop()
     launches = eng.stats()['kernel_launches'] - l0
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)

@@ -117,7 +117,7 @@ struct rri_handle_s {
     int hb = 0, gbw = 0;
     void *ypart = nullptr, *ppart = nullptr, *gpart = nullptr, *hpart = nullptr, *stat = nullptr;
     // hals order
-    void *Xt = nullptr; int64_t ldxt = 0;
+    void *Xt = nullptr; int64_t ldxt = 0, ldwt = 0;
     void *Wt = nullptr, *Tt = nullptr, *Cpart = nullptr, *cg = nullptr /* [max(n,d)*k | k*k] */, *Hm = nullptr;
     void *gram_part = nullptr, *colsum_part = nullptr;
     int splits_t = 1, splits_w = 1, ub_blocks_t = 1, ub_blocks_w = 1, gchunks_w = 1, gchunks_t = 1;
@@ -236,7 +236,11 @@ static int bind_impl(rri_handle_t h, cudaStream_t st)
         const int64_t m = n > d ? n : d;
         if (ws_alloc(h, &h->cg, es * ((size_t)m * k + (size_t)k * k))) return 1;
         if (ws_alloc(h, &h->Hm, es * (size_t)k * k)) return 1;
-        if (ws_alloc(h, &h->Wt, es * (size_t)k * n) || ws_alloc(h, &h->Tt, es * (size_t)d * k)) return 1;
+        {   // rows of W' are TMA operands in tf32 mode: keep them 16-byte aligned
+            const int64_t v = 16 / (int64_t)es;
+            h->ldwt = (n + v - 1) / v * v;
+        }
+        if (ws_alloc(h, &h->Wt, es * (size_t)k * h->ldwt) || ws_alloc(h, &h->Tt, es * (size_t)d * k)) return 1;
         h->gchunks_w = gram_chunks(n, k, h->sm_count);
         h->gchunks_t = gram_chunks(d, k, h->sm_count);
         const int gc = h->gchunks_w > h->gchunks_t ? h->gchunks_w : h->gchunks_t;
@@ -338,6 +342,23 @@ static int rri_prologue(rri_handle_t h, T* W, int t0, const rri_params_t* p, cud
 }
 
 template <typename T>
+static int rri_finish(rri_handle_t h, int t_last, cudaStream_t st)
+{
+    // the sum of the last updated W column has no consumer kernel: finalize it here
+    if (h->world > 1) {
+        launch_reduce_stat<T>((const T*)h->ppart, 0, 0, (const T*)h->gpart, h->gbw, h->k, (T*)h->stat, st);
+        if (allreduce(h, h->stat, (size_t)(h->k + 1), st)) return 1;
+        launch_finalize_sums<T>((const T*)h->stat, 1, h->k, t_last, h->sums, h->flags, st);
+        h->launches += 2;
+    } else {
+        launch_finalize_sums<T>((const T*)h->gpart, h->gbw, h->k, t_last, h->sums, h->flags, st);
+        h->launches++;
+    }
+    CKL();
+    return 0;
+}
+
+template <typename T>
 static int rri_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, bool first_has_prev,
                            const rri_params_t* p, cudaStream_t st)
 {
@@ -346,7 +367,7 @@ static int rri_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, bool fir
     const SolveArgs at = solve_args(p, true), aw = solve_args(p, false);
     for (int t = t0; t < t1; ++t) {
         const int tn = (t + 1) % k;
-        const int t_prev = (t == t0 && !first_has_prev) ? -1 : (t + k - 1) % k;
+        const int t_prev = ((t == t0 && !first_has_prev) || k == 1) ? -1 : (t + k - 1) % k;
         const T* pp = (const T*)h->ppart; int rg = h->pp.rg;
         const T* gp = (const T*)h->gpart; int gb = h->gbw;
         if (h->world > 1) {
@@ -364,28 +385,17 @@ static int rri_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, bool fir
             launch_rri_tstep<T>(Tm, d, k, t, pp, rg, d, gp, gb, at, (T*)h->hpart, h->sums, -1, h->flags, false, st);
             h->launches += 2;
         }
+        // k == 1: the look-ahead statistic p = w_tn'X would be taken from the column this very topic is
+        // about to overwrite, so it is recomputed after the W-step instead
         launch_rri_pass<T>((const T*)h->X, h->ldx, n, d, Tm + (int64_t)t * d, W, k, tn, (T*)h->ypart,
-                           (T*)h->ppart, true, true, h->pp, st);
+                           (T*)h->ppart, true, k > 1, h->pp, st);
         launch_rri_wstep<T>(W, n, k, t, tn, (const T*)h->ypart, h->pp.ct, n, (const T*)h->hpart, h->hb, aw,
                             (T*)h->gpart, h->sums, h->flags, true, h->gbw, st);
         h->launches += 3;
-    }
-    CKL();
-    return 0;
-}
-
-template <typename T>
-static int rri_finish(rri_handle_t h, int t_last, cudaStream_t st)
-{
-    // the sum of the last updated W column has no consumer kernel: finalize it here
-    if (h->world > 1) {
-        launch_reduce_stat<T>((const T*)h->ppart, 0, 0, (const T*)h->gpart, h->gbw, h->k, (T*)h->stat, st);
-        if (allreduce(h, h->stat, (size_t)(h->k + 1), st)) return 1;
-        launch_finalize_sums<T>((const T*)h->stat, 1, h->k, t_last, h->sums, h->flags, st);
-        h->launches += 2;
-    } else {
-        launch_finalize_sums<T>((const T*)h->gpart, h->gbw, h->k, t_last, h->sums, h->flags, st);
-        h->launches++;
+        if (k == 1) {
+            if (rri_finish<T>(h, 0, st)) return 1;
+            if (rri_prologue<T>(h, W, 0, p, st)) return 1;
+        }
     }
     CKL();
     return 0;
@@ -423,7 +433,7 @@ static int hals_W_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, bool 
     }
     const int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_w;
     launch_update_rows<T>(W, n, k, (const T*)h->Cpart, parts, n * k, (const T*)h->Hm, solve_args(p, false),
-                          (T*)h->Wt, (T*)h->colsum_part, h->flags, h->ub_blocks_w, st);
+                          (T*)h->Wt, h->ldwt, (T*)h->colsum_part, h->flags, h->ub_blocks_w, st);
     launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_w, k, h->sums, k, h->world > 1 ? 0 : 2, h->flags, st);
     h->launches += 2;
     if (h->world > 1) {
@@ -445,7 +455,7 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
     T* G = cg + (size_t)d * k;
     launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, G, st);
     h->launches += 2;
-    if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, n, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
+    if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
     const T* C = (const T*)h->Cpart;
     int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_t;
     if (h->world > 1) {
@@ -455,7 +465,7 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
         C = cg; parts = 1;
     }
     // Tt (d x k) is updated in place; its transpose is written straight into the caller's T (k x d)
-    launch_update_rows<T>((T*)h->Tt, d, k, C, parts, d * k, G, solve_args(p, true), Tm, (T*)h->colsum_part,
+    launch_update_rows<T>((T*)h->Tt, d, k, C, parts, d * k, G, solve_args(p, true), Tm, d, (T*)h->colsum_part,
                           h->flags, h->ub_blocks_t, st);
     launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_t, k, h->sums, 0, 1, h->flags, st);
     h->launches += 2;
@@ -542,7 +552,7 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
     }
     if (h->order == RRI_ORDER_HALS) {
         launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
-        launch_transpose<T>(W, n, k, k, (T*)h->Wt, n, st);
+        launch_transpose<T>(W, n, k, k, (T*)h->Wt, h->ldwt, st);
         h->launches += 2;
         for (int s = 0; s < n_sweeps; ++s) {
             if (hals_T_half<T>(h, W, Tm, p, st)) return 1;
@@ -767,7 +777,7 @@ static int profile_impl(rri_handle_t h, int which, const T* W, const T* Tm, int 
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     if (which == 2 && h->mk == MK_NONE && h->order == RRI_ORDER_HALS) {
-        launch_transpose<T>(W, n, k, k, (T*)h->Wt, n, st);
+        launch_transpose<T>(W, n, k, k, (T*)h->Wt, h->ldwt, st);
         h->launches++;
     }
     for (int it = -1; it < iters; ++it) {          // one untimed warm-up launch
@@ -781,7 +791,7 @@ static int profile_impl(rri_handle_t h, int which, const T* W, const T* Tm, int 
             if (contraction<T>(h, (const T*)h->X, h->ldx, Tm, d, (T*)h->Cpart, n, k, d, h->splits_w, st)) return 1;
         } else if (which == 2) {
             if (h->mk != MK_NONE || h->order != RRI_ORDER_HALS) return fail("which=2 needs an unmasked hals-order handle");
-            if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, n, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
+            if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
         } else {
             return fail("bad kernel selector %d", which);
         }

@@ -42,15 +42,13 @@ RRI_DEVINL void part_range(int64_t n, int parts, int p, int64_t& b, int64_t& e) 
 // Scalar-c projected solve of optimization.py:51-67 applied to one element:
 //   numer = (statistic - reg_l1)  [= -w of qf_min], denom = c.
 //   c > 0 : x = max(numer,0)/(c+eps)                       (:53-55; ub ignored)
-//   c <= 0: x = ub if (c - numer) < 0 and ub given, else 0  (:60-65); unbounded -> flag (:66-67)
+//   c <= 0: with ub: x = ub where (c - numer) < 0, else 0    (:60-65)
+//           without ub the reference raises unconditionally  (:66-67 -> :105-107) -> flag
 template <typename T>
 RRI_DEVINL T solve_scalar_c(T numer, T denom, T eps, T ub, bool has_ub, bool& unbounded) {
     if (denom > T(0)) return tmax(numer, T(0)) / (denom + eps);
-    if ((denom - numer) < T(0)) {
-        if (has_ub) return ub;
-        unbounded = true;
-    }
-    return T(0);
+    if (!has_ub) { unbounded = true; return T(0); }
+    return ((denom - numer) < T(0)) ? ub : T(0);
 }
 
 // Vector-c solve of optimization.py:75-84 for one element (masked WRRI): zero where c<=0, clip to ub.

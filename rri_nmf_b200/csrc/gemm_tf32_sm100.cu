@@ -1,9 +1,473 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// gemm_tf32_sm100.cu -- tall-skinny TF32 contraction on the 5th-generation tensor cores (sm_100a).
+//
+//     C[M, N] = A[M, K] * B[N, K]^T          A, B row-major with K contiguous, fp32 in HBM
+//
+// This is the streaming contraction of a block-order half-step (BASELINE.json north_star group (1)):
+//   W half-step:  A = X  (n x d), B = T  (k x d)  ->  X T'   (n x k)
+//   T half-step:  A = X' (d x n), B = W' (k x n)  ->  X' W   (d x k)
+// N = k <= 256 is tiny, so the kernel is bound by reading A once from HBM; at k = 64 the 32 flop/byte
+// it needs (210 TFLOP/s at 6.5 TB/s) is above the FP32 SIMT peak, hence tcgen05.mma kind::tf32.
+//
+// Design
+//   * persistent grid, one CTA per SM, 192 threads = 6 warps: warp 0 TMA producer, warp 1 TMEM owner +
+//     single-thread MMA issuer, warps 2-5 epilogue (one per TMEM lane quarter);
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, zero fill out of bounds) into
+//     a ring of NS stages: A stage = MT x 128 rows x 32 fp32, B stage = NPAD rows x 32 fp32.  The B tile
+//     (whole factor slab for this K chunk) is shared by the MT row tiles a CTA works on at once, so the
+//     factor is re-read from L2 only once per MT*128 rows of A; A uses an evict-first L2 policy, B evict-last;
+//   * accumulators live in TMEM: MT tiles of 128 lanes x NPAD fp32 columns;
+//   * stream-K work split: the (row super-tile, K chunk) units are divided evenly over the CTAs, so every
+//     SM streams the same number of bytes whatever M is (no wave quantisation at 157 or 196 tiles).
+//     A CTA whose segment covers a full K range writes C directly; first/last partial segments go to a
+//     per-CTA slot and a small fix-up kernel adds them in CTA order (deterministic, no float atomics).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "gemm_tf32_sm100.h"
+
 namespace rri {
-struct Tf32Gemm { int dummy; };
-Tf32Gemm* tf32_gemm_create(int, int, std::string& err) { err = "tcgen05 contraction not built yet"; return nullptr; }
-void tf32_gemm_destroy(Tf32Gemm* g) { delete g; }
-int tf32_gemm_run(Tf32Gemm*, const float*, int64_t, const float*, int64_t, float*, int64_t, int64_t, int, int64_t,
-                  cudaStream_t, std::string& err) { err = "tcgen05 contraction not built yet"; return -1; }
+
+namespace {
+
+constexpr int BM = 128;            // rows per UMMA (M of the instruction, cta_group::1)
+constexpr int BK = 32;             // fp32 elements per 128-byte swizzle row
+constexpr int UK = 8;              // K of one tcgen05.mma kind::tf32
+constexpr int THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 4;      // 16 KB
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct GemmParams {
+    int64_t M, K;
+    int N, NPAD;
+    int64_t n_super, nk, units;    // work: n_super row super-tiles x nk K-chunks
+    float* C;
+    int64_t ldc;
+    float* ws;                     // [grid][2][MT*BM*N] partial slots
+    int stages;
+    int tmem_cols;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) {       // ~4 s
+            if (err) atomicExch(err, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, 128-byte swizzle (sm_100 "version 1" format):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups   [46,48) version = 1
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = npad
+__device__ __forceinline__ uint32_t make_idesc(int npad)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// balanced split of `units` over `parts`: first unit of part c
+__host__ __device__ __forceinline__ int64_t part_start(int64_t units, int parts, int64_t c)
+{
+    const int64_t q = units / parts, r = units % parts;
+    return c * q + (c < r ? c : r);
+}
+__host__ __device__ __forceinline__ int64_t part_of(int64_t units, int parts, int64_t u)
+{
+    const int64_t q = units / parts, r = units % parts;
+    if (u < r * (q + 1)) return u / (q + 1);
+    return r + (u - r * (q + 1)) / q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------------
+template <int MT>
+__global__ void __launch_bounds__(THREADS, 1)
+tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p, int* err)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [A stages][B stages][barriers][tmem ptr]
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_stage = MT * A_TILE_BYTES;
+    const int b_stage = p.NPAD * BK * 4;
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + (size_t)p.stages * a_stage;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smB + (size_t)p.stages * b_stage);
+    uint64_t* empty = full + p.stages;
+    uint64_t* tfull = empty + p.stages;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t u_begin = part_start(p.units, gridDim.x, blockIdx.x);
+    const int64_t u_end = part_start(p.units, gridDim.x, blockIdx.x + 1);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            const uint64_t polA = policy_evict_first(), polB = policy_evict_last();
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t u = u_begin; u < u_end;) {
+                const int64_t s = u / p.nk, kc0 = u % p.nk;
+                const int64_t len = (u_end - u) < (p.nk - kc0) ? (u_end - u) : (p.nk - kc0);
+                for (int64_t kc = kc0; kc < kc0 + len; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1, err, 1);
+                    mbar_expect_tx(&full[stage], (uint32_t)(a_stage + b_stage));
+                    tma_load_2d(&tmA, smA + (size_t)stage * a_stage, &full[stage], (int)(kc * BK), (int)(s * MT * BM), polA);
+                    tma_load_2d(&tmB, smB + (size_t)stage * b_stage, &full[stage], (int)(kc * BK), 0, polB);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                u += len;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =======================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(p.NPAD);
+            int stage = 0; uint32_t phase = 0, tphase = 0;
+            for (int64_t u = u_begin; u < u_end;) {
+                const int64_t kc0 = u % p.nk;
+                const int64_t len = (u_end - u) < (p.nk - kc0) ? (u_end - u) : (p.nk - kc0);
+                mbar_wait(tempty, tphase ^ 1, err, 2);           // epilogue has drained the accumulators
+                tc_fence_after();
+                for (int64_t i = 0; i < len; ++i) {
+                    mbar_wait(&full[stage], phase, err, 3);      // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(smA + (size_t)stage * a_stage);
+                    const uint32_t b0 = smem_u32(smB + (size_t)stage * b_stage);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                        for (int ks = 0; ks < BK / UK; ++ks) {
+                            const uint64_t ad = make_desc(a0 + mt * A_TILE_BYTES + ks * UK * 4);
+                            const uint64_t bd = make_desc(b0 + ks * UK * 4);
+                            umma_tf32(tmem_base + (uint32_t)(mt * p.NPAD), ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[stage]);                   // frees the smem slot when the MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull);                               // accumulators complete
+                tphase ^= 1;
+                u += len;
+            }
+        }
+    } else {
+        // ===================================== epilogue =========================================
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        uint32_t tphase = 0;
+        const int64_t slot_elems = (int64_t)MT * BM * p.N;
+        for (int64_t u = u_begin; u < u_end;) {
+            const int64_t s = u / p.nk, kc0 = u % p.nk;
+            const int64_t len = (u_end - u) < (p.nk - kc0) ? (u_end - u) : (p.nk - kc0);
+            const bool complete = (len == p.nk);
+            float* dst; int64_t ld; int64_t row_base; int64_t row_limit;
+            if (complete) { dst = p.C; ld = p.ldc; row_base = s * MT * BM; row_limit = p.M; }
+            else {
+                const int slot = (u == u_begin) ? 0 : 1;
+                dst = p.ws + ((int64_t)blockIdx.x * 2 + slot) * slot_elems; ld = p.N; row_base = 0; row_limit = MT * BM;
+            }
+            mbar_wait(tfull, tphase, err, 4);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int64_t row = row_base + mt * BM + q * 32 + lane;
+                const bool rok = row < row_limit;
+                for (int c0 = 0; c0 < p.NPAD; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NPAD + c0), v);
+                    if (rok) {
+                        float* o = dst + row * ld + c0;
+                        if ((c0 + 16 <= p.N) && ((ld & 3) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (c0 + j < p.N) o[j] = v[j];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+            tphase ^= 1;
+            u += len;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// adds the partial segments of every split row super-tile in CTA order
+template <int MT>
+__global__ void tf32_gemm_fixup_kernel(GemmParams p, int grid_main)
+{
+    const int64_t s = blockIdx.x;
+    const int64_t u0 = s * p.nk, u1 = u0 + p.nk;
+    const int64_t c_lo = part_of(p.units, grid_main, u0), c_hi = part_of(p.units, grid_main, u1 - 1);
+    if (c_lo == c_hi) return;                                     // written directly by one CTA
+    const int64_t slot_elems = (int64_t)MT * BM * p.N;
+    for (int64_t e = threadIdx.x; e < slot_elems; e += blockDim.x) {
+        const int64_t r = e / p.N, c = e % p.N;
+        const int64_t row = s * MT * BM + r;
+        if (row >= p.M) break;
+        float acc = 0.f;
+        for (int64_t cta = c_lo; cta <= c_hi; ++cta) {
+            const int slot = part_start(p.units, grid_main, cta) >= u0 ? 0 : 1;
+            acc += p.ws[(cta * 2 + slot) * slot_elems + e];
+        }
+        p.C[row * p.ldc + c] = acc;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct Tf32Gemm {
+    int sm_count = 148;
+    int nmax = 0;
+    EncodeTiledFn encode = nullptr;
+    float* ws = nullptr;
+    size_t ws_bytes = 0;
+    int* err = nullptr;
+    CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+    int force_mt = 0;
+};
+
+Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
+{
+    Tf32Gemm* g = new Tf32Gemm();
+    g->sm_count = sm_count;
+    g->nmax = nmax;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        err = "cuTensorMapEncodeTiled is not available from the driver";
+        delete g;
+        return nullptr;
+    }
+    g->encode = (EncodeTiledFn)fn;
+    // per-CTA partial slots: 2 x (MT*128 x N) floats, MT <= 2
+    g->ws_bytes = (size_t)sm_count * 2 * 2 * BM * (size_t)((nmax + 15) / 16 * 16) * sizeof(float);
+    if (cudaMalloc(&g->ws, g->ws_bytes) != cudaSuccess || cudaMalloc(&g->err, sizeof(int)) != cudaSuccess) {
+        err = "workspace allocation failed";
+        delete g;
+        return nullptr;
+    }
+    cudaMemset(g->err, 0, sizeof(int));
+    // operand element type seen by TMA: TFLOAT32 (default) or plain FLOAT32 (RRI_TMA_F32=1), for the
+    // rounding experiment described in DESIGN.md
+    const char* ev = getenv("RRI_TMA_F32");
+    if (ev && ev[0] == '1') g->dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const char* mt = getenv("RRI_GEMM_MT");
+    if (mt) g->force_mt = atoi(mt);
+    return g;
+}
+
+void tf32_gemm_destroy(Tf32Gemm* g)
+{
+    if (!g) return;
+    if (g->ws) cudaFree(g->ws);
+    if (g->err) cudaFree(g->err);
+    delete g;
+}
+
+static bool encode_2d(Tf32Gemm* g, CUtensorMap* tm, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                      int box_rows, std::string& err)
+{
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 4) % 16 != 0) {
+        err = "TMA needs 16-byte aligned rows (leading dimension multiple of 4 floats, base 16-byte aligned)";
+        return false;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g->encode(tm, g->dtype, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%d)", (int)r,
+                 (long long)rows, (long long)cols, (long long)ld, box_rows);
+        err = buf;
+        return false;
+    }
+    return true;
+}
+
+template <int MT>
+static int run_mt(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t st, std::string& err)
+{
+    const int a_stage = MT * A_TILE_BYTES, b_stage = p.NPAD * BK * 4;
+    const int bar_bytes = 1024;
+    int stages = (SMEM_LIMIT - 1024 /*alignment slack*/ - bar_bytes) / (a_stage + b_stage);
+    if (stages > 8) stages = 8;
+    if (stages < 2) { err = "not enough shared memory for two pipeline stages"; return -1; }
+    p.stages = stages;
+    const size_t smem = (size_t)stages * (a_stage + b_stage) + bar_bytes + 1024;
+    int cols = 32;
+    while (cols < MT * p.NPAD) cols <<= 1;
+    p.tmem_cols = cols;
+    int64_t grid = p.units < g->sm_count ? p.units : g->sm_count;
+    auto kern = tf32_gemm_kernel<MT>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        err = "cudaFuncSetAttribute(max dynamic smem) failed";
+        return -1;
+    }
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(tmA, tmB, p, g->err);
+    tf32_gemm_fixup_kernel<MT><<<(unsigned)p.n_super, 256, 0, st>>>(p, (int)grid);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = cudaGetErrorString(e); return -1; }
+    return 2;
+}
+
+int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                  int64_t M, int N, int64_t K, cudaStream_t st, std::string& err)
+{
+    if (!g) { err = "null contraction handle"; return -1; }
+    if (N < 1 || N > 256) { err = "N must be in [1,256]"; return -1; }
+    const int npad = (N + 15) / 16 * 16;
+    if (npad > (g->nmax + 15) / 16 * 16) { err = "N exceeds the rank this handle was created for"; return -1; }
+    int mt = (M > BM) ? 2 : 1;
+    if (mt * npad > 512) mt = 1;
+    if (g->force_mt == 1 || g->force_mt == 2) mt = (g->force_mt * npad <= 512) ? g->force_mt : 1;
+    CUtensorMap tmA, tmB;
+    if (!encode_2d(g, &tmA, A, M, K, lda, mt * BM, err)) return -1;
+    if (!encode_2d(g, &tmB, B, N, K, ldb, npad, err)) return -1;
+    GemmParams p;
+    p.M = M; p.K = K; p.N = N; p.NPAD = npad;
+    p.n_super = (M + (int64_t)mt * BM - 1) / ((int64_t)mt * BM);
+    p.nk = (K + BK - 1) / BK;
+    p.units = p.n_super * p.nk;
+    p.C = C; p.ldc = ldc; p.ws = g->ws;
+    p.stages = 0; p.tmem_cols = 0;
+    return mt == 2 ? run_mt<2>(g, tmA, tmB, p, st, err) : run_mt<1>(g, tmA, tmB, p, st, err);
+}
+
+}  // namespace rri

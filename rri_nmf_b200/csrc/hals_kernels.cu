@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(U_THREADS)
 update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cpart, int parts,
                    int64_t part_stride, const T* __restrict__ S,
                    T reg_l1, T reg_l2, T eps, T ub, int has_ub,
-                   T* __restrict__ Ft, T* __restrict__ colsum_part, int* __restrict__ flags)
+                   T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* ftile = reinterpret_cast<T*>(smem_raw);                 // [k][U_GROUP+1]
@@ -212,7 +212,7 @@ update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cp
             __syncthreads();
             for (int e = tid; e < k * U_GROUP; e += U_THREADS) {
                 const int tp = e / U_GROUP, ii = e % U_GROUP;
-                if (i0 + ii < m) Ft[(int64_t)tp * m + i0 + ii] = ftile[tp * (U_GROUP + 1) + ii];
+                if (i0 + ii < m) Ft[(int64_t)tp * ldft + i0 + ii] = ftile[tp * (U_GROUP + 1) + ii];
             }
             __syncthreads();
         }
@@ -234,8 +234,8 @@ update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cp
 
 template <typename T, int KL>
 static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
-                                  const T* S, const SolveArgs& a, T* Ft, T* colsum_part, int* flags,
-                                  int blocks, cudaStream_t st)
+                                  const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
+                                  int* flags, int blocks, cudaStream_t st)
 {
     size_t base = sizeof(T) * ((size_t)k * (U_GROUP + 1) + (size_t)U_NW * k);
     size_t with_s = base + sizeof(T) * (size_t)k * k;
@@ -243,27 +243,27 @@ static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int pa
         auto kern = update_rows_kernel<T, KL, true>;
         if (with_s > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_s);
         kern<<<blocks, U_THREADS, with_s, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1,
-                                                 (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft,
+                                                 (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft,
                                                  colsum_part, flags);
     } else {
         auto kern = update_rows_kernel<T, KL, false>;
         if (base > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
         kern<<<blocks, U_THREADS, base, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1,
-                                               (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft,
+                                               (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft,
                                                colsum_part, flags);
     }
 }
 
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
-                        const T* S, const SolveArgs& a, T* Ft, T* colsum_part, int* flags, int blocks,
-                        cudaStream_t st)
+                        const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part, int* flags,
+                        int blocks, cudaStream_t st)
 {
     const int kl = (k + 31) / 32;
-    if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
-    else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
-    else if (kl <= 4) launch_update_rows_kl<T, 4>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
-    else launch_update_rows_kl<T, 8>(F, m, k, Cpart, parts, part_stride, S, a, Ft, colsum_part, flags, blocks, st);
+    if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    else if (kl <= 4) launch_update_rows_kl<T, 4>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    else launch_update_rows_kl<T, 8>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,7 +422,7 @@ void launch_transpose(const T* A, int64_t rows, int64_t cols, int64_t lda, T* B,
     template void launch_simt_gemm_nt<T>(const T*, int64_t, const T*, int64_t, T*, int64_t, int, int64_t, \
                                          int, cudaStream_t);                                              \
     template void launch_update_rows<T>(T*, int64_t, int, const T*, int, int64_t, const T*,               \
-                                        const SolveArgs&, T*, T*, int*, int, cudaStream_t);               \
+                                        const SolveArgs&, T*, int64_t, T*, int*, int, cudaStream_t);      \
     template void launch_gram<T>(const T*, int64_t, int, T*, int, T*, cudaStream_t);                      \
     template void launch_reduce_parts<T>(const T*, int, int64_t, int64_t, T*, cudaStream_t);              \
     template void launch_colsum_finalize<T>(const T*, int, int, double*, int, int, int*, cudaStream_t);   \

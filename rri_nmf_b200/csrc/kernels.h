@@ -73,8 +73,8 @@ void launch_simt_gemm_nt(const T* A, int64_t lda, const T* B, int64_t ldb, T* Cp
 int update_rows_blocks(int64_t m, int sm_count);
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
-                        const T* S, const SolveArgs& a, T* Ft, T* colsum_part, int* flags, int blocks,
-                        cudaStream_t st);
+                        const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part, int* flags,
+                        int blocks, cudaStream_t st);
 
 // Gram matrix G[k,k] = F'F of a row-major F[m,k]: per-chunk partials + fixed-order finalize.
 int gram_chunks(int64_t m, int k, int sm_count);

@@ -170,10 +170,13 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         own_engine = engine is None
         if engine is None:
             engine = RRIEngine(Xd, k, W_mat=Md, order=update_order, math=math, comm=comm)
+        keep = False
         try:
-            return _solve(engine, Xd, W, T, rtv, locals())
+            out = _solve(engine, Xd, W, T, rtv, locals())
+            keep = 'obj_calculator' in out        # the returned objective calculator owns the engine
+            return out
         finally:
-            if own_engine:
+            if own_engine and not keep:
                 engine.close()
 
 
