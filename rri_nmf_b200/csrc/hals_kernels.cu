@@ -114,7 +114,7 @@ constexpr int U_THREADS = 256, U_NW = U_THREADS / WARP, U_GROUP = 32;   // rows 
 
 int update_rows_blocks(int64_t m, int sm_count)
 {
-    int64_t b = (m + U_GROUP - 1) / U_GROUP;
+    int64_t b = (m + 127) / 128;
     if (b > 4 * sm_count) b = 4 * sm_count;
     return (int)(b < 1 ? 1 : b);
 }
@@ -254,11 +254,120 @@ static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int pa
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// row update, thread per row (k <= KM): the row's k factor entries live in registers (static
+// indices only), the Gram row S[t,:] is a shared-memory broadcast read with 16-byte loads, the
+// contraction row C[i,:] sits in a padded shared tile.  Direct form, as the reference computes it:
+//     numer_t = C[i,t] - sum_{j != t} F[i,j] S[j,t]        (nmf.py:733 / :675 with the current factor)
+// Rows are staged through shared memory so that global traffic stays coalesced.
+// ------------------------------------------------------------------------------------------------
+constexpr int TPR_ROWS = 128;       // rows (= threads) per block
+
+template <typename T, int KM>
+__global__ void __launch_bounds__(TPR_ROWS)
+update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cpart, int parts,
+                       int64_t part_stride, const T* __restrict__ S,
+                       T reg_l1, T reg_l2, T eps, T ub, int has_ub,
+                       T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags)
+{
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    constexpr int LD = KM + 1;                              // padded row stride of the tiles
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Ss = reinterpret_cast<T*>(smem_raw);                 // [KM][KM], zero padded, 16-byte aligned rows
+    T* ctile = Ss + KM * KM;                                // [TPR_ROWS][LD]  contraction rows
+    T* ftile = ctile + TPR_ROWS * LD;                       // [TPR_ROWS][LD]  factor rows
+    const int tid = threadIdx.x;
+    for (int e = tid; e < KM * KM; e += TPR_ROWS) {
+        const int a = e / KM, b = e % KM;
+        Ss[e] = (a < k && b < k) ? S[a * k + b] : T(0);
+    }
+    T csum = T(0);          // thread j < k accumulates the sum of column j over this block's rows
+    bool unb = false;
+    __syncthreads();
+
+    const int64_t ngroups = (m + TPR_ROWS - 1) / TPR_ROWS;
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t i0 = g * TPR_ROWS;
+        const int nrow = (int)((m - i0) < TPR_ROWS ? (m - i0) : TPR_ROWS);
+        for (int64_t e = tid; e < (int64_t)nrow * k; e += TPR_ROWS) {
+            T c = T(0);
+            for (int p = 0; p < parts; ++p) c += Cpart[(int64_t)p * part_stride + i0 * k + e];
+            const int rr = (int)(e / k), cc = (int)(e % k);
+            ctile[rr * LD + cc] = c;
+            ftile[rr * LD + cc] = F[i0 * k + e];
+        }
+        __syncthreads();
+        T f[KM];
+#pragma unroll
+        for (int j = 0; j < KM; ++j) f[j] = (j < k && tid < nrow) ? ftile[tid * LD + j] : T(0);
+        if (tid < nrow) {
+#pragma unroll 1
+            for (int t = 0; t < k; ++t) {
+                const V* srow = reinterpret_cast<const V*>(Ss + t * KM);
+                T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+                for (int jv = 0; jv < KM / VN; ++jv) {
+                    T sv[VN];
+                    unpack(srow[jv], sv);
+#pragma unroll
+                    for (int v = 0; v < VN; ++v) acc[(jv * VN + v) & 3] = fma(f[jv * VN + v], sv[v], acc[(jv * VN + v) & 3]);
+                }
+                const T stt = Ss[t * KM + t];
+                const T ft = ftile[tid * LD + t];
+                // sum over j != t: remove the own term from the full dot product
+                const T dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
+                const T x = solve_scalar_c<T>(ctile[tid * LD + t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
+                ftile[tid * LD + t] = x;
+#pragma unroll
+                for (int j = 0; j < KM; ++j) f[j] = (j == t) ? x : f[j];
+            }
+        }
+        __syncthreads();
+        if (tid < k) {
+            T cs = T(0);
+            for (int ii = 0; ii < nrow; ++ii) cs += ftile[ii * LD + tid];
+            csum += cs;
+        }
+        for (int64_t e = tid; e < (int64_t)nrow * k; e += TPR_ROWS) F[i0 * k + e] = ftile[(e / k) * LD + (e % k)];
+        if (Ft) {
+            for (int e = tid; e < k * TPR_ROWS; e += TPR_ROWS) {
+                const int tp = e / TPR_ROWS, ii = e % TPR_ROWS;
+                if (ii < nrow) Ft[(int64_t)tp * ldft + i0 + ii] = ftile[ii * LD + tp];
+            }
+        }
+        __syncthreads();
+    }
+    if (unb) atomicOr(flags, 4);
+    if (tid < k) colsum_part[(int64_t)blockIdx.x * k + tid] = csum;
+}
+
+template <typename T, int KM>
+static void launch_update_rows_tpr(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
+                                   const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
+                                   int* flags, int blocks, cudaStream_t st)
+{
+    const size_t smem = sizeof(T) * ((size_t)KM * KM + 2 * (size_t)TPR_ROWS * (KM + 1));
+    auto kern = update_rows_tpr_kernel<T, KM>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<blocks, TPR_ROWS, smem, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1, (T)a.reg_l2,
+                                        (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft, colsum_part, flags);
+}
+
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
                         const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part, int* flags,
                         int blocks, cudaStream_t st)
 {
+    // thread-per-row variants while the row fits in registers / the tiles in shared memory
+    // (fp32: k <= 128, fp64: k <= 64); wider ranks use the warp-per-row kernel
+#define RRI_TPR(KM) launch_update_rows_tpr<T, KM>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st)
+    if (k <= 16) { RRI_TPR(16); return; }
+    if (k <= 32) { RRI_TPR(32); return; }
+    if (k <= 64) { RRI_TPR(64); return; }
+    if (k <= 128 && sizeof(T) == 4) { RRI_TPR(128); return; }
+#undef RRI_TPR
     const int kl = (k + 31) / 32;
     if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
     else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);

@@ -1,0 +1,21 @@
+"""Multi-GPU parity: launches tests/multi_gpu_check.py on 2 ranks when the box has >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_rank_row_sharded_parity(cuda_device):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29511',
+                        os.path.join(ROOT, 'tests', 'multi_gpu_check.py')],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=600)
+    assert 'MULTI_GPU_PARITY PASS' in r.stdout, r.stdout[-3000:]
