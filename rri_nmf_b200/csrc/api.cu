@@ -563,7 +563,7 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
     if (rri_prologue<T>(h, W, 0, p, st)) return 1;
     for (int s = 0; s < n_sweeps; ++s)
         if (rri_topic_range<T>(h, W, Tm, 0, k, s > 0, p, st)) return 1;
-    return rri_finish<T>(h, k - 1, st);
+    return k == 1 ? 0 : rri_finish<T>(h, k - 1, st);     // (k == 1 finalises inside the topic loop)
 }
 
 static int read_flags(rri_handle_t h, int32_t* flags_host, cudaStream_t st)
@@ -605,7 +605,7 @@ static int topics_impl(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri_pa
     }
     if (rri_prologue<T>(h, W, t0, p, st)) return 1;
     if (rri_topic_range<T>(h, W, Tm, t0, t1, false, p, st)) return 1;
-    return rri_finish<T>(h, t1 - 1, st);
+    return h->k == 1 ? 0 : rri_finish<T>(h, t1 - 1, st);
 }
 
 extern "C" int rri_topics(rri_handle_t h, void* W_dev, void* T_dev, int32_t t_begin, int32_t t_end,

@@ -320,25 +320,32 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
-// adds the partial segments of every split row super-tile in CTA order
+// adds the partial segments of every split row super-tile in CTA order.  A stream-K split over G CTAs
+// cuts at most G-1 super-tiles, so the grid is one block per CTA boundary: boundary b (between CTA b and
+// b+1) owns the super-tile that contains unit part_start(b+1) -- if that unit is not a tile start and no
+// earlier boundary falls into the same tile.
 template <int MT>
-__global__ void tf32_gemm_fixup_kernel(GemmParams p, int grid_main)
+__global__ void __launch_bounds__(256)
+tf32_gemm_fixup_kernel(GemmParams p, int grid_main)
 {
-    const int64_t s = blockIdx.x;
+    const int64_t ub = part_start(p.units, grid_main, (int64_t)blockIdx.x + 1);   // first unit of CTA b+1
+    if (ub % p.nk == 0) return;                                   // the cut falls on a tile boundary
+    const int64_t s = ub / p.nk;
     const int64_t u0 = s * p.nk, u1 = u0 + p.nk;
     const int64_t c_lo = part_of(p.units, grid_main, u0), c_hi = part_of(p.units, grid_main, u1 - 1);
-    if (c_lo == c_hi) return;                                     // written directly by one CTA
-    const int64_t slot_elems = (int64_t)MT * BM * p.N;
-    for (int64_t e = threadIdx.x; e < slot_elems; e += blockDim.x) {
-        const int64_t r = e / p.N, c = e % p.N;
-        const int64_t row = s * MT * BM + r;
-        if (row >= p.M) break;
+    if (c_lo != (int64_t)blockIdx.x) return;                      // an earlier boundary owns this tile
+    const int slot_elems = MT * BM * p.N;
+    const int64_t row0 = s * MT * BM;
+    const int rows = (int)((p.M - row0) < (int64_t)MT * BM ? (p.M - row0) : (int64_t)MT * BM);
+    const int nvalid = rows * p.N;
+    for (int e = threadIdx.x; e < nvalid; e += blockDim.x) {
         float acc = 0.f;
         for (int64_t cta = c_lo; cta <= c_hi; ++cta) {
             const int slot = part_start(p.units, grid_main, cta) >= u0 ? 0 : 1;
-            acc += p.ws[(cta * 2 + slot) * slot_elems + e];
+            acc += p.ws[(cta * 2 + slot) * (int64_t)slot_elems + e];
         }
-        p.C[row * p.ldc + c] = acc;
+        const int r = e / p.N, c = e - r * p.N;
+        p.C[(row0 + r) * p.ldc + c] = acc;
     }
 }
 
@@ -441,7 +448,7 @@ static int run_mt(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, G
         return -1;
     }
     kern<<<(unsigned)grid, THREADS, smem, st>>>(tmA, tmB, p, g->err);
-    tf32_gemm_fixup_kernel<MT><<<(unsigned)p.n_super, 256, 0, st>>>(p, (int)grid);
+    if (grid > 1) tf32_gemm_fixup_kernel<MT><<<(unsigned)(grid - 1), 256, 0, st>>>(p, (int)grid);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return -1; }
     return 2;

@@ -465,17 +465,20 @@ void launch_gram(const T* F, int64_t m, int k, T* part, int chunks, T* G, cudaSt
 }
 
 template <typename T>
-__global__ void colsum_finalize_kernel(const T* __restrict__ colsum_part, int blocks, int k,
-                                       double* __restrict__ sums, int off, int zero_flag,
-                                       int* __restrict__ flags)
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const T* __restrict__ colsum_part, int blocks, int k, double* __restrict__ sums,
+                       int off, int zero_flag, int* __restrict__ flags)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < k) {
-        T s = T(0);
-        for (int b = 0; b < blocks; ++b) s += colsum_part[(int64_t)b * k + t];
+    // one warp per column; lanes stride over the block partials, fixed-order shuffle tree
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= k) return;
+    T s = T(0);
+    for (int b = lane; b < blocks; b += 32) s += colsum_part[(int64_t)b * k + warp];
+    s = warp_sum(s);
+    if (lane == 0) {
         const double v = (double)s;
-        sums[off + t] = v;
-        if (!(v > 1e-10)) atomicOr(flags, zero_flag);
+        sums[off + warp] = v;
+        if (zero_flag && !(v > 1e-10)) atomicOr(flags, zero_flag);
         if (!isfinite(v)) atomicOr(flags, 8);
     }
 }
@@ -484,7 +487,7 @@ template <typename T>
 void launch_colsum_finalize(const T* colsum_part, int blocks, int k, double* sums, int off,
                             int zero_flag, int* flags, cudaStream_t st)
 {
-    colsum_finalize_kernel<T><<<(k + 127) / 128, 128, 0, st>>>(colsum_part, blocks, k, sums, off, zero_flag, flags);
+    colsum_finalize_kernel<T><<<(k * 32 + 255) / 256, 256, 0, st>>>(colsum_part, blocks, k, sums, off, zero_flag, flags);
 }
 
 // ------------------------------------------------------------------------------------------------

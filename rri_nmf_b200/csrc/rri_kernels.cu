@@ -23,19 +23,23 @@ constexpr int MAX_NCH = 5;
 // ------------------------------------------------------------------------------------------------
 // streaming pass
 // ------------------------------------------------------------------------------------------------
+// Every WARP owns a column slice of width 32*VEC*NCH (its T_t slice and p accumulators live in
+// registers) and walks the rows of its row group PASS_RU at a time; the row dot products are finished
+// with warp shuffles and written as per-slice partials ypart[slice][row].  No shared memory and no
+// block barrier: the 8 warps of a CTA (and the 2 CTAs of an SM) drift freely, which keeps ~160 KB of
+// 16-byte streaming loads in flight per SM.
 template <typename T, int VEC, int NCH>
 __global__ void __launch_bounds__(PASS_THREADS, 2)
 rri_pass_kernel(const T* __restrict__ X, int64_t ldx, int64_t n, int64_t d,
                 const T* __restrict__ tvec, const T* __restrict__ W, int k, int tn,
-                T* __restrict__ ypart, T* __restrict__ ppart, int do_y, int do_p)
+                T* __restrict__ ypart, T* __restrict__ ppart, int do_y, int do_p, int n_slices)
 {
     using V = typename Vec<T>::type;
     constexpr int NW = PASS_THREADS / WARP;
-    __shared__ T red[2][NW][PASS_RU];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t cw = (int64_t)PASS_THREADS * VEC * NCH;
-    const int64_t c0 = blockIdx.x * cw;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slice = blockIdx.x * NW + warp;
+    if (slice >= n_slices) return;
+    const int64_t c0 = (int64_t)slice * (WARP * VEC * NCH);
     int64_t r0, r1;
     part_range(n, gridDim.y, blockIdx.y, r0, r1);
 
@@ -44,7 +48,7 @@ rri_pass_kernel(const T* __restrict__ X, int64_t ldx, int64_t n, int64_t d,
     T tv[NCH][VEC], pacc[NCH][VEC];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
-        col[j] = c0 + ((int64_t)j * PASS_THREADS + tid) * VEC;
+        col[j] = c0 + ((int64_t)j * WARP + lane) * VEC;
         cok[j] = col[j] < d;                       // d % VEC == 0 on the vector path
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
@@ -53,8 +57,7 @@ rri_pass_kernel(const T* __restrict__ X, int64_t ldx, int64_t n, int64_t d,
         }
     }
 
-    int it = 0;
-    for (int64_t i = r0; i < r1; i += PASS_RU, ++it) {
+    for (int64_t i = r0; i < r1; i += PASS_RU) {
         T x[PASS_RU][NCH][VEC];
         T wv[PASS_RU];
 #pragma unroll
@@ -91,19 +94,13 @@ rri_pass_kernel(const T* __restrict__ X, int64_t ldx, int64_t n, int64_t d,
             ys[r] = s;
         }
         if (do_y) {
+            T mine = T(0);
 #pragma unroll
-            for (int r = 0; r < PASS_RU; ++r) ys[r] = warp_sum(ys[r]);
-            if (lane == 0) {
-#pragma unroll
-                for (int r = 0; r < PASS_RU; ++r) red[it & 1][warp][r] = ys[r];
+            for (int r = 0; r < PASS_RU; ++r) {
+                const T tot = warp_sum(ys[r]);
+                if (lane == r) mine = tot;
             }
-            __syncthreads();
-            if (tid < PASS_RU && (i + tid) < r1) {
-                T s = T(0);
-#pragma unroll
-                for (int w = 0; w < NW; ++w) s += red[it & 1][w][tid];
-                ypart[(int64_t)blockIdx.x * n + i + tid] = s;
-            }
+            if (lane < PASS_RU && (i + lane) < r1) ypart[(int64_t)slice * n + i + lane] = mine;
         }
     }
     if (do_p) {
@@ -123,13 +120,18 @@ PassPlan plan_pass(int64_t n, int64_t d, int64_t ldx, const void* X, int elem_si
     const int vmax = 16 / elem_size;
     const bool aligned = (d % vmax == 0) && (ldx % vmax == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
     pl.vec = aligned ? vmax : 1;
-    const int64_t chunk = (int64_t)PASS_THREADS * pl.vec;           // columns covered by one chunk
-    pl.ct = (int)((d + chunk * MAX_NCH - 1) / (chunk * MAX_NCH));
-    pl.nch = (int)((d + chunk * pl.ct - 1) / (chunk * pl.ct));
+    const int64_t chunk = (int64_t)WARP * pl.vec;                    // columns one warp covers per chunk
+    const int NW = PASS_THREADS / WARP;
+    // number of CTAs along the columns with the widest slices, then the narrowest slice that still covers d
+    const int64_t cta_cols = chunk * MAX_NCH * NW;
+    const int ctas_x = (int)((d + cta_cols - 1) / cta_cols);
+    pl.nch = (int)((d + chunk * NW * ctas_x - 1) / (chunk * NW * ctas_x));
     if (pl.nch < 1) pl.nch = 1;
-    pl.cw = chunk * pl.nch;
+    pl.cw = chunk * pl.nch;                                           // slice width
+    pl.ct = (int)((d + pl.cw - 1) / pl.cw);                           // number of warp slices = y partials per row
     int target = 2 * sm_count;                                        // two resident CTAs per SM
-    pl.rg = target / pl.ct;
+    const int gx = (pl.ct + NW - 1) / NW;
+    pl.rg = target / gx;
     if (pl.rg < 1) pl.rg = 1;
     int64_t max_rg = (n + PASS_RU - 1) / PASS_RU;
     if (pl.rg > max_rg) pl.rg = (int)(max_rg < 1 ? 1 : max_rg);
@@ -141,11 +143,11 @@ static void launch_pass_vec(const T* X, int64_t ldx, int64_t n, int64_t d, const
                             int k, int tn, T* ypart, T* ppart, bool do_y, bool do_p,
                             const PassPlan& pl, cudaStream_t st)
 {
-    dim3 grid(pl.ct, pl.rg);
+    dim3 grid((pl.ct + PASS_THREADS / WARP - 1) / (PASS_THREADS / WARP), pl.rg);
 #define RRI_PASS_CASE(N)                                                                      \
     case N:                                                                                   \
         rri_pass_kernel<T, VEC, N><<<grid, PASS_THREADS, 0, st>>>(X, ldx, n, d, tvec, W, k, tn, \
-                                                                   ypart, ppart, do_y, do_p);  \
+                                                                   ypart, ppart, do_y, do_p, pl.ct); \
         break;
     switch (pl.nch) {
         RRI_PASS_CASE(1) RRI_PASS_CASE(2) RRI_PASS_CASE(3) RRI_PASS_CASE(4) RRI_PASS_CASE(5)
@@ -307,33 +309,56 @@ rri_wstep_kernel(T* __restrict__ W, int64_t n, int k, int t, int tn,
     bool unb = false;
     const T denom = nt + reg_l2;
 
-    for (int64_t i = r0 + warp; i < r1; i += NW) {
-        T wrow[KL];
+    // RW rows per warp iteration: their loads are independent, so the L2 round trips overlap
+    constexpr int RW = 4;
+    for (int64_t ib = r0 + (int64_t)warp * RW; ib < r1; ib += (int64_t)NW * RW) {
+        T wrow[RW][KL], yv[RW], sv[RW];
 #pragma unroll
-        for (int l = 0; l < KL; ++l) {
-            const int j = lane + 32 * l;
-            wrow[l] = (j < k) ? W[i * k + j] : T(0);
+        for (int q = 0; q < RW; ++q) {
+            const int64_t i = ib + q;
+            const bool rok = i < r1;
+#pragma unroll
+            for (int l = 0; l < KL; ++l) {
+                const int j = lane + 32 * l;
+                wrow[q][l] = (rok && j < k) ? W[i * k + j] : T(0);
+            }
+            T y = T(0);
+            if (do_update && rok)
+                for (int c = lane; c < ct; c += WARP) y += ypart[(int64_t)c * ystride + i];
+            yv[q] = y;
         }
         if (do_update) {
-            T s = T(0);
 #pragma unroll
-            for (int l = 0; l < KL; ++l) s = fma(wrow[l], hreg[l], s);
-            s = warp_sum(s);
-            T y = T(0);
-            for (int c = 0; c < ct; ++c) y += ypart[(int64_t)c * ystride + i];
-            const T x = solve_scalar_c<T>(y - s - reg_l1, denom, eps, ub, has_ub != 0, unb);
-            xsum += x;
+            for (int q = 0; q < RW; ++q) {
+                T s = T(0);
+#pragma unroll
+                for (int l = 0; l < KL; ++l) s = fma(wrow[q][l], hreg[l], s);
+                sv[q] = s;
+            }
+#pragma unroll
+            for (int q = 0; q < RW; ++q) { sv[q] = warp_sum(sv[q]); yv[q] = warp_sum(yv[q]); }
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                const int64_t i = ib + q;
+                if (i < r1) {
+                    const T x = solve_scalar_c<T>(yv[q] - sv[q] - reg_l1, denom, eps, ub, has_ub != 0, unb);
+                    xsum += x;
+#pragma unroll
+                    for (int l = 0; l < KL; ++l)
+                        if (lane + 32 * l == t) { wrow[q][l] = x; W[i * k + t] = x; }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < RW; ++q) {
+            T wsel = T(0);
 #pragma unroll
             for (int l = 0; l < KL; ++l)
-                if (lane + 32 * l == t) { wrow[l] = x; W[i * k + t] = x; }
+                if (l == (tn >> 5)) wsel = wrow[q][l];
+            const T wtn = __shfl_sync(0xffffffffu, wsel, tn & 31);
+#pragma unroll
+            for (int l = 0; l < KL; ++l) gacc[l] = fma(wtn, wrow[q][l], gacc[l]);
         }
-        T wsel = T(0);
-#pragma unroll
-        for (int l = 0; l < KL; ++l)
-            if (l == (tn >> 5)) wsel = wrow[l];
-        const T wtn = __shfl_sync(0xffffffffu, wsel, tn & 31);
-#pragma unroll
-        for (int l = 0; l < KL; ++l) gacc[l] = fma(wtn, wrow[l], gacc[l]);
     }
     if (unb) atomicOr(flags, 4);
 
