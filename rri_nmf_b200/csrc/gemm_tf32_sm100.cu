@@ -338,14 +338,32 @@ tf32_gemm_fixup_kernel(GemmParams p, int grid_main)
     const int64_t row0 = s * MT * BM;
     const int rows = (int)((p.M - row0) < (int64_t)MT * BM ? (p.M - row0) : (int64_t)MT * BM);
     const int nvalid = rows * p.N;
-    for (int e = threadIdx.x; e < nvalid; e += blockDim.x) {
-        float acc = 0.f;
-        for (int64_t cta = c_lo; cta <= c_hi; ++cta) {
-            const int slot = part_start(p.units, grid_main, cta) >= u0 ? 0 : 1;
-            acc += p.ws[(cta * 2 + slot) * (int64_t)slot_elems + e];
+    // slot base of every contributing CTA, computed once (64-bit divisions are slow)
+    __shared__ const float* src[160];
+    const int ncontrib = (int)(c_hi - c_lo + 1);
+    for (int i = threadIdx.x; i < ncontrib; i += blockDim.x) {
+        const int64_t cta = c_lo + i;
+        const int slot = part_start(p.units, grid_main, cta) >= u0 ? 0 : 1;
+        src[i] = p.ws + (cta * 2 + slot) * (int64_t)slot_elems;
+    }
+    __syncthreads();
+    float* dst = p.C + row0 * p.ldc;
+    if (p.ldc == p.N && (nvalid & 3) == 0) {
+        for (int e = threadIdx.x * 4; e < nvalid; e += blockDim.x * 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < ncontrib; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(src[i] + e);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            *reinterpret_cast<float4*>(dst + e) = acc;
         }
-        const int r = e / p.N, c = e - r * p.N;
-        p.C[(row0 + r) * p.ldc + c] = acc;
+    } else {
+        for (int e = threadIdx.x; e < nvalid; e += blockDim.x) {
+            float acc = 0.f;
+            for (int i = 0; i < ncontrib; ++i) acc += src[i][e];
+            const int r = e / p.N, c = e - r * p.N;
+            dst[(int64_t)r * p.ldc + c] = acc;
+        }
     }
 }
 

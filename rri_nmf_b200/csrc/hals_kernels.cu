@@ -291,12 +291,43 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
     for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
         const int64_t i0 = g * TPR_ROWS;
         const int nrow = (int)((m - i0) < TPR_ROWS ? (m - i0) : TPR_ROWS);
-        for (int64_t e = tid; e < (int64_t)nrow * k; e += TPR_ROWS) {
-            T c = T(0);
-            for (int p = 0; p < parts; ++p) c += Cpart[(int64_t)p * part_stride + i0 * k + e];
-            const int rr = (int)(e / k), cc = (int)(e % k);
-            ctile[rr * LD + cc] = c;
-            ftile[rr * LD + cc] = F[i0 * k + e];
+        {   // coalesced staging of the C and F rows, 8 independent loads in flight per thread (a plain loop
+            // serialises one L2 round trip per element); (row, col) of e = tid + 128*it advance without divisions
+            const int tot = nrow * k;
+            int rr = tid / k, cc = tid - rr * k;
+            const int dr = TPR_ROWS / k, dc = TPR_ROWS - dr * k;
+            const T* Frow = F + i0 * k;
+            const T* Crow = Cpart + i0 * k;
+            constexpr int UB = 8;
+            for (int e0 = tid; e0 < tot; e0 += UB * TPR_ROWS) {
+                T cv[UB], fv[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int e = e0 + u * TPR_ROWS;
+                    cv[u] = T(0); fv[u] = T(0);
+                    if (e < tot) {
+                        cv[u] = Crow[e];
+                        fv[u] = Frow[e];
+                    }
+                }
+                for (int p = 1; p < parts; ++p) {
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const int e = e0 + u * TPR_ROWS;
+                        if (e < tot) cv[u] += Crow[(int64_t)p * part_stride + e];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int e = e0 + u * TPR_ROWS;
+                    if (e < tot) {
+                        ctile[rr * LD + cc] = cv[u];
+                        ftile[rr * LD + cc] = fv[u];
+                    }
+                    rr += dr; cc += dc;
+                    if (cc >= k) { cc -= k; ++rr; }
+                }
+            }
         }
         __syncthreads();
         T f[KM];
@@ -325,16 +356,27 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
             }
         }
         __syncthreads();
-        if (tid < k) {
-            T cs = T(0);
-            for (int ii = 0; ii < nrow; ++ii) cs += ftile[ii * LD + tid];
-            csum += cs;
-        }
-        for (int64_t e = tid; e < (int64_t)nrow * k; e += TPR_ROWS) F[i0 * k + e] = ftile[(e / k) * LD + (e % k)];
-        if (Ft) {
-            for (int e = tid; e < k * TPR_ROWS; e += TPR_ROWS) {
-                const int tp = e / TPR_ROWS, ii = e % TPR_ROWS;
-                if (ii < nrow) Ft[(int64_t)tp * ldft + i0 + ii] = ftile[ii * LD + tp];
+        {   // write back: F (row-major, coalesced), column sums, transposed copy
+            const int tot = nrow * k;
+            int rr = tid / k, cc = tid - rr * k;
+            const int dr = TPR_ROWS / k, dc = TPR_ROWS - dr * k;
+            T* Frow = F + i0 * k;
+            for (int e = tid; e < tot; e += TPR_ROWS) {
+                Frow[e] = ftile[rr * LD + cc];
+                rr += dr; cc += dc;
+                if (cc >= k) { cc -= k; ++rr; }
+            }
+            // column sums: TPR_ROWS/KM-way split of the rows per column when the block has spare threads
+            if (tid < k) {
+                T cs = T(0);
+#pragma unroll 8
+                for (int ii = 0; ii < nrow; ++ii) cs += ftile[ii * LD + tid];
+                csum += cs;
+            }
+            if (Ft) {
+                // thread ii writes element (tp, i0+ii): consecutive threads -> consecutive addresses
+                if (tid < nrow)
+                    for (int tp = 0; tp < k; ++tp) Ft[(int64_t)tp * ldft + i0 + tid] = ftile[tid * LD + tp];
             }
         }
         __syncthreads();
@@ -449,10 +491,28 @@ __global__ void reduce_parts_kernel(const T* __restrict__ part, int parts, int64
     }
 }
 
+// same sum with one warp per output element (lanes stride over the parts, fixed shuffle tree):
+// for short outputs with many parts (Gram partials) the serial version is latency-bound
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduce_parts_warp_kernel(const T* __restrict__ part, int parts, int64_t stride, int64_t len, T* __restrict__ out)
+{
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= len) return;
+    T s = T(0);
+    for (int p = lane; p < parts; p += 32) s += part[(int64_t)p * stride + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s;
+}
+
 template <typename T>
 void launch_reduce_parts(const T* part, int parts, int64_t stride, int64_t len, T* out, cudaStream_t st)
 {
-    reduce_parts_kernel<T><<<(unsigned)((len + 255) / 256), 256, 0, st>>>(part, parts, stride, len, out);
+    if (parts >= 16 && len <= 65536)
+        reduce_parts_warp_kernel<T><<<(unsigned)((len * 32 + 255) / 256), 256, 0, st>>>(part, parts, stride, len, out);
+    else
+        reduce_parts_kernel<T><<<(unsigned)((len + 255) / 256), 256, 0, st>>>(part, parts, stride, len, out);
 }
 
 template <typename T>

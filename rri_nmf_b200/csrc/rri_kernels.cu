@@ -187,6 +187,7 @@ rri_tstep_kernel(T* __restrict__ Tm, int64_t d, int k, int t,
 
     for (int j = tid; j < ks; j += TS_THREADS) {
         T s = T(0);
+#pragma unroll 8
         for (int b = 0; b < gb; ++b) s += gpart[(int64_t)b * ks + j];
         gs[j] = s;
     }
@@ -204,10 +205,14 @@ rri_tstep_kernel(T* __restrict__ Tm, int64_t d, int k, int t,
     if (c < d) {
         if (do_update) {
             T p = T(0);
+#pragma unroll 8
             for (int r = 0; r < rg; ++r) p += ppart[(int64_t)r * pstride + c];
             T dot = T(0);
-            for (int j = 0; j < k; ++j)
-                if (j != t) dot = fma(gs[j], Tm[(int64_t)j * d + c], dot);
+#pragma unroll 8
+            for (int j = 0; j < k; ++j) {
+                const T tj = Tm[(int64_t)j * d + c];
+                dot = fma(j != t ? gs[j] : T(0), tj, dot);
+            }
             bool unb = false;
             x = solve_scalar_c<T>(p - dot - reg_l1, gs[t] + reg_l2, eps, ub, has_ub != 0, unb);
             if (unb) atomicOr(flags, 4);
@@ -278,6 +283,7 @@ rri_wstep_kernel(T* __restrict__ W, int64_t n, int k, int t, int tn,
     if (do_update) {
         for (int j = tid; j < ks; j += WS_THREADS) {
             T s = T(0);
+#pragma unroll 8
             for (int b = 0; b < hb; ++b) s += hpart[(int64_t)b * ks + j];
             hs[j] = s;
         }
