@@ -10,6 +10,7 @@
 #include "../../include/rri_b200.h"
 #include "gemm_tf32_sm100.h"
 #include "kernels.h"
+#include "wrri_tc_sm100.h"
 
 using namespace rri;
 
@@ -126,6 +127,7 @@ struct rri_handle_s {
     // masked
     TilePlan tpl{}, wpl{};
     void *numer_part = nullptr, *denom_part = nullptr, *mstat = nullptr;
+    WrriTc* wtc = nullptr; int wtc_groups_t = 1, wtc_groups_w = 1;
     // common
     double* sums = nullptr;    // [2k] device
     int* flags = nullptr;      // device
@@ -181,6 +183,7 @@ extern "C" int rri_destroy(rri_handle_t h)
     cudaSetDevice(h->device);
     for (void* p : h->allocs) cudaFree(p);
     if (h->tf32) tf32_gemm_destroy(h->tf32);
+    if (h->wtc) wrri_tc_destroy(h->wtc);
     delete h;
     return 0;
 }
@@ -219,7 +222,18 @@ static int bind_impl(rri_handle_t h, cudaStream_t st)
         if (!h->numer_part) {
             h->tpl = plan_tstats(n, d, h->sm_count);
             h->wpl = plan_wstats(n, d, h->sm_count);
-            const size_t a = (size_t)h->tpl.groups * d, b = (size_t)h->wpl.groups * n;
+            size_t a = (size_t)h->tpl.groups * d, b = (size_t)h->wpl.groups * n;
+            if (h->math == RRI_MATH_TF32) {
+                // fp32 data: the W T product of every tile goes through the tensor cores
+                std::string err;
+                h->wtc = wrri_tc_create(h->sm_count, n, d, k, err);
+                if (!h->wtc) return fail("tensor-core WRRI path unavailable: %s", err.c_str());
+                h->wtc_groups_t = wrri_tc_groups(h->wtc, 0);
+                h->wtc_groups_w = wrri_tc_groups(h->wtc, 1);
+                const size_t a2 = (size_t)h->wtc_groups_t * d, b2 = (size_t)h->wtc_groups_w * n;
+                if (a2 > a) a = a2;
+                if (b2 > b) b = b2;
+            }
             const size_t m = a > b ? a : b;
             if (ws_alloc(h, &h->numer_part, es * m) || ws_alloc(h, &h->denom_part, es * m)) return 1;
             if (ws_alloc(h, &h->mstat, es * 2 * (size_t)d)) return 1;
@@ -480,11 +494,19 @@ template <typename T>
 static int wrri_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, cudaStream_t st)
 {
     const int64_t n = h->n, d = h->d;
-    launch_wrri_tstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, n, d, h->k, t, (T*)h->numer_part,
-                          (T*)h->denom_part, h->tpl, st);
+    int parts = h->tpl.groups;
+    if (h->wtc) {
+        std::string err;
+        parts = h->wtc_groups_t;
+        if (wrri_tc_stats(h->wtc, 0, (const float*)h->X, h->ldx, h->M, h->mk, h->ldm, t, (float*)h->numer_part,
+                          (float*)h->denom_part, parts, st, err) < 0)
+            return fail("tensor-core WRRI T statistics failed: %s", err.c_str());
+    } else {
+        launch_wrri_tstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, n, d, h->k, t, (T*)h->numer_part,
+                              (T*)h->denom_part, h->tpl, st);
+    }
     h->launches++;
     const T* nu = (const T*)h->numer_part; const T* de = (const T*)h->denom_part;
-    int parts = h->tpl.groups;
     if (h->world > 1) {
         T* ms = (T*)h->mstat;
         launch_reduce_parts<T>(nu, parts, d, d, ms, st);
@@ -493,7 +515,9 @@ static int wrri_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p
         if (allreduce(h, ms, (size_t)2 * d, st)) return 1;
         nu = ms; de = ms + d; parts = 1;
     }
-    launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), Tm + (int64_t)t * d, 1, h->flags, st);
+    T* tp2 = h->wtc ? (T*)wrri_tc_Tp(h->wtc) + t : nullptr;       // keep the padded T' operand in step
+    launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), Tm + (int64_t)t * d, 1, tp2,
+                         h->wtc ? wrri_tc_KP(h->wtc) : 0, h->flags, st);
     launch_vec_sum_flag<T>(Tm + (int64_t)t * d, d, 1, h->sums, t, 1, h->flags, st);
     h->launches += 2;
     return 0;
@@ -503,10 +527,20 @@ template <typename T>
 static int wrri_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, cudaStream_t st)
 {
     const int64_t n = h->n, d = h->d;
-    launch_wrri_wstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, n, d, h->k, t, (T*)h->numer_part,
-                          (T*)h->denom_part, h->wpl, st);
-    launch_wrri_final<T>((const T*)h->numer_part, (const T*)h->denom_part, h->wpl.groups, n, solve_args(p, false),
-                         W + t, h->k, h->flags, st);
+    int parts = h->wpl.groups;
+    if (h->wtc) {
+        std::string err;
+        parts = h->wtc_groups_w;
+        if (wrri_tc_stats(h->wtc, 1, (const float*)h->X, h->ldx, h->M, h->mk, h->ldm, t, (float*)h->numer_part,
+                          (float*)h->denom_part, parts, st, err) < 0)
+            return fail("tensor-core WRRI W statistics failed: %s", err.c_str());
+    } else {
+        launch_wrri_wstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, n, d, h->k, t, (T*)h->numer_part,
+                              (T*)h->denom_part, h->wpl, st);
+    }
+    T* wp2 = h->wtc ? (T*)wrri_tc_Wp(h->wtc) + t : nullptr;       // keep the padded W operand in step
+    launch_wrri_final<T>((const T*)h->numer_part, (const T*)h->denom_part, parts, n, solve_args(p, false),
+                         W + t, h->k, wp2, h->wtc ? wrri_tc_KP(h->wtc) : 0, h->flags, st);
     launch_vec_sum_flag<T>(W + t, n, h->k, h->sums, h->k + t, h->world > 1 ? 0 : 2, h->flags, st);
     h->launches += 3;
     if (h->world > 1) {
@@ -527,6 +561,7 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
     const int k = h->k;
     const int64_t n = h->n, d = h->d;
     if (h->mk != MK_NONE) {
+        if (h->wtc) { wrri_tc_load_factors(h->wtc, (const float*)W, (const float*)Tm, st); h->launches += 2; }
         for (int s = 0; s < n_sweeps; ++s) {
             if (h->order == RRI_ORDER_RRI) {
                 for (int t = 0; t < k; ++t) {
@@ -596,6 +631,7 @@ template <typename T>
 static int topics_impl(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri_params_t* p, cudaStream_t st)
 {
     if (h->mk != MK_NONE) {
+        if (h->wtc) { wrri_tc_load_factors(h->wtc, (const float*)W, (const float*)Tm, st); h->launches += 2; }
         for (int t = t0; t < t1; ++t) {
             if (wrri_T_step<T>(h, W, Tm, t, p, st)) return 1;
             if (wrri_W_step<T>(h, W, Tm, t, p, st)) return 1;

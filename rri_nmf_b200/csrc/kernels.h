@@ -119,9 +119,11 @@ void launch_wrri_wstats(const T* X, int64_t ldx, const void* M, int mk, int64_t 
                         const T* Tm, int64_t n, int64_t d, int k, int t, T* numer_part, T* denom_part,
                         const TilePlan& pl, cudaStream_t st);
 // vector-c solve (optimization.py:75-84) of out[idx*stride] for idx < len from `parts` partial slices
+// (out2/out2_stride: optional second destination -- the padded operand copy of the tensor-core path)
 template <typename T>
 void launch_wrri_final(const T* numer_part, const T* denom_part, int parts, int64_t len,
-                       const SolveArgs& a, T* out, int64_t out_stride, int* flags, cudaStream_t st);
+                       const SolveArgs& a, T* out, int64_t out_stride, T* out2, int64_t out2_stride,
+                       int* flags, cudaStream_t st);
 // sums[slot] = sum_i v[i*stride]; zero/non-finite flags (single block, fixed order)
 template <typename T>
 void launch_vec_sum_flag(const T* v, int64_t len, int64_t stride, double* sums, int slot, int zero_flag,

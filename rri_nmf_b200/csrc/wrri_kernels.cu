@@ -225,26 +225,31 @@ void launch_wrri_wstats(const T* X, int64_t ldx, const void* M, int mk, int64_t 
 template <typename T>
 __global__ void wrri_final_kernel(const T* __restrict__ numer_part, const T* __restrict__ denom_part,
                                   int parts, int64_t len, T reg_l1, T reg_l2, T eps, T ub, int has_ub,
-                                  T* __restrict__ out, int64_t out_stride, int* __restrict__ flags)
+                                  T* __restrict__ out, int64_t out_stride, T* __restrict__ out2,
+                                  int64_t out2_stride, int* __restrict__ flags)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= len) return;
     T nu = T(0), de = T(0);
+#pragma unroll 4
     for (int p = 0; p < parts; ++p) {
         nu += numer_part[(int64_t)p * len + i];
         de += denom_part[(int64_t)p * len + i];
     }
     bool unb = false;
-    out[i * out_stride] = solve_vector_c<T>(nu - reg_l1, de + reg_l2, eps, ub, has_ub != 0, unb);
+    const T x = solve_vector_c<T>(nu - reg_l1, de + reg_l2, eps, ub, has_ub != 0, unb);
+    out[i * out_stride] = x;
+    if (out2) out2[i * out2_stride] = x;
     if (unb) atomicOr(flags, 4);
 }
 
 template <typename T>
 void launch_wrri_final(const T* numer_part, const T* denom_part, int parts, int64_t len,
-                       const SolveArgs& a, T* out, int64_t out_stride, int* flags, cudaStream_t st)
+                       const SolveArgs& a, T* out, int64_t out_stride, T* out2, int64_t out2_stride,
+                       int* flags, cudaStream_t st)
 {
     wrri_final_kernel<T><<<(unsigned)((len + 255) / 256), 256, 0, st>>>(numer_part, denom_part, parts, len,
-        (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, out, out_stride, flags);
+        (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, out, out_stride, out2, out2_stride, flags);
 }
 
 template <typename T>
@@ -410,7 +415,7 @@ void launch_norms(const T* v, int64_t len, double* part, double* out, cudaStream
     template void launch_wrri_wstats<T>(const T*, int64_t, const void*, int, int64_t, const T*, const T*,   \
                                         int64_t, int64_t, int, int, T*, T*, const TilePlan&, cudaStream_t); \
     template void launch_wrri_final<T>(const T*, const T*, int, int64_t, const SolveArgs&, T*, int64_t,     \
-                                       int*, cudaStream_t);                                                 \
+                                       T*, int64_t, int*, cudaStream_t);                                    \
     template void launch_vec_sum_flag<T>(const T*, int64_t, int64_t, double*, int, int, int*, cudaStream_t);\
     template void launch_vec_scale_to_sum<T>(T*, int64_t, int64_t, const double*, int, double, cudaStream_t);\
     template void launch_objective<T>(const T*, int64_t, const void*, int, int64_t, const T*, const T*,     \

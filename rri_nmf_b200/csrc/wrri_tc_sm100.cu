@@ -1,0 +1,511 @@
+// wrri_tc_sm100.cu -- masked / weighted WRRI half-step statistics with the W T product on the tensor
+// cores (sm_100a, fp32 data, TF32 operands).
+//
+// Reference arithmetic (src/rri_nmf/nmf.py:687-701 and :735-746), for topic t:
+//     R      = M o (X - W_{t->0} T)                                   (never materialised here)
+//     T-step : numer[c] = sum_i W[i,t] R[i,c]      denom[c] = sum_i W[i,t]^2 M[i,c]
+//     W-step : numer[i] = sum_c R[i,c] T[t,c]      denom[i] = sum_c M[i,c] T[t,c]^2
+// The SIMT kernels of wrri_kernels.cu spend k FMAs per matrix element on the CUDA cores.  Here every
+// 128x128 tile of W T is one burst of tcgen05.mma kind::tf32 (K = k padded to 32) into TMEM; the
+// epilogue warps move it to shared memory and then walk X and the mask in their own row-major,
+// fully coalesced order, adding topic t back in fp32 (W_{t->0}T = WT - w_t T_t).  With a sparse
+// mask the X loads of all-masked 16-byte groups are skipped, so the pass reads the mask once and only
+// the observed neighbourhood of X.
+//
+// Operands are engine-owned zero-padded copies Wp[n, KP], Tp[d, KP] (K-contiguous rows of KP = k
+// rounded up to 32 floats -> legal TMA rows and whole 128-byte swizzle atoms).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "kernels.h"
+#include "wrri_tc_sm100.h"
+
+namespace rri {
+
+namespace {
+
+constexpr int TM = 128, TN = 128;          // tile: rows of X x columns of X
+constexpr int BK = 32;                     // floats per 128-byte swizzle row
+constexpr int UK = 8;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (1 + EPI_WARPS);
+constexpr int DS_LD = TN + 4;              // padded row stride of the staged product tile (floats)
+constexpr int OP_CHUNK_BYTES = TM * BK * 4;   // one 32-float K chunk of a 128-row operand tile: 16 KB
+
+struct TcParams {
+    const float* X; int64_t ldx;
+    const void* M; int64_t ldm;
+    const float* Wp; const float* Tp;      // padded operand copies [n,KP], [d,KP]
+    int64_t n, d;
+    int KP, t;
+    int tiles_r, tiles_c;                  // number of 128-row / 128-column tiles
+    int groups;                            // T mode: row groups per column tile; W mode: column groups per row tile
+    float* numer_part; float* denom_part;  // [groups][d] (T mode) or [groups][n] (W mode)
+    int stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();       // a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)      // K-major, SWIZZLE_128B (see gemm_tf32_sm100.cu)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void epi_barrier()     // named barrier 1: the 8 epilogue warps only
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+}
+
+// raw mask word(s) of one 16-byte X group: one 32-bit word of 4 bytes (u8) or one float4 (real weights)
+template <int MK> struct MaskRaw;
+template <> struct MaskRaw<MK_U8> {
+    uint32_t w;
+    __device__ __forceinline__ void load(const void* M, int64_t idx, bool ok)
+    {
+        w = ok ? __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(M) + idx)) : 0u;
+    }
+    __device__ __forceinline__ bool any() const { return w != 0u; }
+    __device__ __forceinline__ void decode(float m[4]) const
+    {
+        m[0] = (float)(w & 0xffu); m[1] = (float)((w >> 8) & 0xffu); m[2] = (float)((w >> 16) & 0xffu); m[3] = (float)(w >> 24);
+    }
+};
+template <> struct MaskRaw<MK_REAL> {
+    float4 v;
+    __device__ __forceinline__ void load(const void* M, int64_t idx, bool ok)
+    {
+        v = ok ? __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(M) + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __device__ __forceinline__ bool any() const { return (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f); }
+    __device__ __forceinline__ void decode(float m[4]) const { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
+};
+
+// MODE 0: T-step statistics (column sums; CTA = one column tile x one row group)
+// MODE 1: W-step statistics (row sums;    CTA = one row tile    x one column group)
+template <int MODE, int MK>
+__global__ void __launch_bounds__(THREADS, 1)
+wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT, TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int nchunk = p.KP / BK;
+    const int op_bytes = nchunk * OP_CHUNK_BYTES;           // one 128-row operand tile
+    uint8_t* sm_fixed = smem;                               // the operand that stays for the whole CTA
+    uint8_t* sm_var = smem + op_bytes;                      // [stages] the operand that changes per tile
+    float* Ds = reinterpret_cast<float*>(sm_var + (size_t)p.stages * op_bytes);     // [TM][DS_LD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Ds + TM * DS_LD);
+    uint64_t* fixed_full = bars;            // 1
+    uint64_t* var_full = bars + 1;          // [2]
+    uint64_t* var_free = bars + 3;          // [2]
+    uint64_t* acc_full = bars + 5;          // [2]
+    uint64_t* acc_free = bars + 7;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile walk of this CTA
+    const int fixed_tile = blockIdx.x;      // column tile (MODE 0) / row tile (MODE 1)
+    const int nvar_total = MODE == 0 ? p.tiles_r : p.tiles_c;
+    int vb, ve;
+    {
+        const int q = nvar_total / (int)gridDim.y, r = nvar_total % (int)gridDim.y, g = blockIdx.y;
+        vb = q * g + (g < r ? g : r);
+        ve = vb + q + (g < r ? 1 : 0);
+    }
+    const int ntiles = ve - vb;
+
+    if (threadIdx.x == 0) {
+        mbar_init(fixed_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&var_full[s], 1); mbar_init(&var_free[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA + MMA control thread ================================
+        if (lane == 0 && ntiles > 0) {
+            const CUtensorMap* tm_fixed = MODE == 0 ? &tmT : &tmW;     // MODE 0: column tile of T' is fixed
+            const CUtensorMap* tm_var = MODE == 0 ? &tmW : &tmT;
+            // A operand = W rows (D lanes = rows of X), B operand = T' rows (D columns = columns of X)
+            mbar_expect_tx(fixed_full, (uint32_t)op_bytes);
+            for (int c = 0; c < nchunk; ++c) tma_load_2d(tm_fixed, sm_fixed + c * OP_CHUNK_BYTES, fixed_full, c * BK, fixed_tile * TM);
+            const int S = p.stages;
+            for (int s0 = 0; s0 < S && s0 < ntiles; ++s0) {           // prologue: fill the ring
+                mbar_expect_tx(&var_full[s0], (uint32_t)op_bytes);
+                for (int c = 0; c < nchunk; ++c)
+                    tma_load_2d(tm_var, sm_var + (size_t)s0 * op_bytes + c * OP_CHUNK_BYTES, &var_full[s0], c * BK, (vb + s0) * TM);
+            }
+            mbar_wait(fixed_full, 0);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            for (int n = 0; n < ntiles; ++n) {
+                const int s = n % S, a = n & 1;
+                mbar_wait(&var_full[s], (n / S) & 1);
+                mbar_wait(&acc_free[a], ((n >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t var0 = smem_u32(sm_var + (size_t)s * op_bytes), fix0 = smem_u32(sm_fixed);
+                const uint32_t w0 = MODE == 0 ? var0 : fix0;      // W tile (A)
+                const uint32_t t0 = MODE == 0 ? fix0 : var0;      // T' tile (B)
+                for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+                    for (int ks = 0; ks < BK / UK; ++ks) {
+                        umma_tf32(tmem_base + (uint32_t)(a * TN), make_desc(w0 + c * OP_CHUNK_BYTES + ks * UK * 4),
+                                  make_desc(t0 + c * OP_CHUNK_BYTES + ks * UK * 4), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&var_free[s]);
+                umma_commit(&acc_full[a]);
+                if (n + S < ntiles) {
+                    // refill this stage for tile n+S once the MMAs that read it have retired
+                    mbar_wait(&var_free[s], (n / S) & 1);
+                    mbar_expect_tx(&var_full[s], (uint32_t)op_bytes);
+                    for (int c = 0; c < nchunk; ++c)
+                        tma_load_2d(tm_var, sm_var + (size_t)s * op_bytes + c * OP_CHUNK_BYTES, &var_full[s], c * BK, (vb + n + S) * TM);
+                }
+            }
+        }
+    } else {
+        // ======================================= epilogue ========================================
+        const int ew = warp - 1;                 // 0..7
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        // coalesced element-wise mapping: lane owns 4 consecutive columns, warp ew owns rows ew, ew+8, ...
+        const int cl = 4 * lane;
+        float nacc[MODE == 0 ? 4 : 16], dacc[MODE == 0 ? 4 : 16];
+#pragma unroll
+        for (int i = 0; i < (MODE == 0 ? 4 : 16); ++i) { nacc[i] = 0.f; dacc[i] = 0.f; }
+
+        for (int n = 0; n < ntiles; ++n) {
+            const int a = n & 1;
+            const int rt = MODE == 0 ? (vb + n) : fixed_tile;         // row tile
+            const int ctile = MODE == 0 ? fixed_tile : (vb + n);      // column tile
+            const int64_t i0 = (int64_t)rt * TM, c0 = (int64_t)ctile * TN;
+            const int64_t gc = c0 + cl;
+            const bool cok = gc < p.d;                                // d % 4 == 0 is required by the launcher
+            // the masks do not depend on the product tile: request them before blocking on the MMA
+            MaskRaw<MK> mr[16];
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                const int64_t gi = i0 + ew + 8 * rr;
+                mr[rr].load(p.M, gi * p.ldm + gc, cok && gi < p.n);
+            }
+            float tt[4] = {0.f, 0.f, 0.f, 0.f};
+            if (cok) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) tt[v] = __ldg(p.Tp + (gc + v) * p.KP + p.t);
+            }
+            mbar_wait(&acc_full[a], (n >> 1) & 1);
+            tc_fence_after();
+            {   // TMEM -> shared: the two warps of a lane quarter take 64 columns each
+                const int half = (warp - 1) >> 2;                     // warps 1-4 -> 0, warps 5-8 -> 1
+                const int row = q * 32 + lane;
+#pragma unroll 1
+                for (int cc = 0; cc < 64; cc += 16) {
+                    float v[16];
+                    const int col = half * 64 + cc;
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + col), v);
+                    float4* o = reinterpret_cast<float4*>(Ds + row * DS_LD + col);
+                    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                    o[3] = make_float4(v[12], v[13], v[14], v[15]);
+                }
+            }
+            // observed X groups of this tile: all 16 rows' loads in flight together (one round trip), issued
+            // before the barrier so that part of their latency hides behind it
+            float4 xv[16];
+            float wts[16];
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                const int64_t gi = i0 + ew + 8 * rr;
+                xv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                wts[rr] = 0.f;
+                if (mr[rr].any()) {
+                    xv[rr] = __ldcs(reinterpret_cast<const float4*>(p.X + gi * p.ldx + gc));
+                    wts[rr] = __ldg(p.Wp + gi * p.KP + p.t);
+                }
+            }
+            tc_fence_before();
+            epi_barrier();                                            // product tile staged; TMEM reads done
+            if (lane == 0 && ew < 4) mbar_arrive(&acc_free[a]);
+
+            // ---- element-wise pass in X's own layout
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                if (mr[rr].any()) {
+                    const int r = ew + 8 * rr;
+                    float m[4];
+                    mr[rr].decode(m);
+                    const float4 dv = *reinterpret_cast<const float4*>(Ds + r * DS_LD + cl);
+                    const float wt = wts[rr];
+                    const float x[4] = {xv[rr].x, xv[rr].y, xv[rr].z, xv[rr].w};
+                    const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float res = m[v] * (x[v] - dd[v] + wt * tt[v]);          // M o (X - W_{t->0} T)
+                        if (MODE == 0) {
+                            nacc[v] = fmaf(wt, res, nacc[v]);
+                            dacc[v] = fmaf(wt * wt, m[v], dacc[v]);
+                        } else {
+                            nacc[rr] = fmaf(res, tt[v], nacc[rr]);
+                            dacc[rr] = fmaf(m[v] * tt[v], tt[v], dacc[rr]);
+                        }
+                    }
+                }
+            }
+            epi_barrier();                                            // Ds may be overwritten by the next tile
+        }
+
+        // ---- reductions and partial output
+        if (MODE == 0) {
+            // column sums: add the 8 warps through shared memory (Ds is free now)
+            float* red = Ds;                                          // [8][2][128]
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                red[(ew * 2 + 0) * TN + cl + v] = nacc[v];
+                red[(ew * 2 + 1) * TN + cl + v] = dacc[v];
+            }
+            epi_barrier();
+            const int e = threadIdx.x - 32;                           // 0..255
+            const int which = e >> 7, cc = e & 127;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < EPI_WARPS; ++w) s += red[(w * 2 + which) * TN + cc];
+            const int64_t gcol = (int64_t)fixed_tile * TN + cc;
+            if (gcol < p.d) (which ? p.denom_part : p.numer_part)[(int64_t)blockIdx.y * p.d + gcol] = s;
+        } else {
+            // row sums: lanes hold per-row partials over their column slices
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                float a = nacc[rr], b = dacc[rr];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                const int64_t gi = (int64_t)fixed_tile * TM + ew + 8 * rr;
+                if (lane == 0 && gi < p.n) {
+                    p.numer_part[(int64_t)blockIdx.y * p.n + gi] = a;
+                    p.denom_part[(int64_t)blockIdx.y * p.n + gi] = b;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// dst[r, 0:KP] = (c < cols) ? src[r, c] (or src[c, r] when transposed) : 0
+__global__ void pad_copy_kernel(const float* __restrict__ src, int64_t rows, int cols, int64_t ld, int transposed,
+                                float* __restrict__ dst, int KP)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * KP) return;
+    const int64_t r = e / KP;
+    const int c = (int)(e % KP);
+    float v = 0.f;
+    if (c < cols) v = transposed ? src[(int64_t)c * ld + r] : src[r * ld + c];
+    dst[e] = v;
+}
+
+}  // namespace
+
+struct WrriTc {
+    int sm_count = 148;
+    EncodeTiledFn encode = nullptr;
+    int64_t n = 0, d = 0;
+    int k = 0, KP = 0;
+    float* Wp = nullptr;
+    float* Tp = nullptr;
+    CUtensorMap tmW, tmT;
+    int stages = 2;
+    size_t smem = 0;
+};
+
+WrriTc* wrri_tc_create(int sm_count, int64_t n, int64_t d, int k, std::string& err)
+{
+    if (k > 128) { err = "the tensor-core WRRI path supports k <= 128"; return nullptr; }
+    if (d % 4 != 0) { err = "the tensor-core WRRI path needs d % 4 == 0"; return nullptr; }
+    WrriTc* g = new WrriTc();
+    g->sm_count = sm_count; g->n = n; g->d = d; g->k = k;
+    g->KP = (k + 31) / 32 * 32;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || !fn) {
+        err = "cuTensorMapEncodeTiled is not available from the driver";
+        delete g;
+        return nullptr;
+    }
+    g->encode = (EncodeTiledFn)fn;
+    if (cudaMalloc(&g->Wp, sizeof(float) * (size_t)n * g->KP) != cudaSuccess ||
+        cudaMalloc(&g->Tp, sizeof(float) * (size_t)d * g->KP) != cudaSuccess) {
+        err = "operand copy allocation failed";
+        wrri_tc_destroy(g);
+        return nullptr;
+    }
+    auto enc = [&](CUtensorMap* tm, float* base, int64_t rows) -> bool {
+        cuuint64_t gdim[2] = {(cuuint64_t)g->KP, (cuuint64_t)rows};
+        cuuint64_t gstr[1] = {(cuuint64_t)g->KP * 4};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)TM};
+        cuuint32_t estr[2] = {1, 1};
+        return g->encode(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!enc(&g->tmW, g->Wp, n) || !enc(&g->tmT, g->Tp, d)) {
+        err = "cuTensorMapEncodeTiled failed for the WRRI operands";
+        wrri_tc_destroy(g);
+        return nullptr;
+    }
+    const int op_bytes = (g->KP / BK) * OP_CHUNK_BYTES;
+    g->stages = g->KP <= 64 ? 2 : 1;
+    g->smem = (size_t)op_bytes * (1 + g->stages) + sizeof(float) * TM * DS_LD + 256 + 1024;
+    return g;
+}
+
+void wrri_tc_destroy(WrriTc* g)
+{
+    if (!g) return;
+    if (g->Wp) cudaFree(g->Wp);
+    if (g->Tp) cudaFree(g->Tp);
+    delete g;
+}
+
+float* wrri_tc_Wp(WrriTc* g) { return g->Wp; }
+float* wrri_tc_Tp(WrriTc* g) { return g->Tp; }
+int wrri_tc_KP(WrriTc* g) { return g->KP; }
+
+int wrri_tc_groups(WrriTc* g, int mode)
+{
+    const int tiles_r = (int)((g->n + TM - 1) / TM), tiles_c = (int)((g->d + TN - 1) / TN);
+    const int fixed = mode == 0 ? tiles_c : tiles_r, var = mode == 0 ? tiles_r : tiles_c;
+    // enough CTAs for ~8 waves of one CTA per SM, at least 4 tiles per CTA when there are that many
+    int groups = (8 * g->sm_count + fixed - 1) / fixed;
+    if (groups > (var + 3) / 4) groups = (var + 3) / 4;
+    if (groups < 1) groups = 1;
+    return groups;
+}
+
+// refresh the padded operand copies from the caller's factors (start of a call)
+void wrri_tc_load_factors(WrriTc* g, const float* W, const float* T, cudaStream_t st)
+{
+    int64_t e = g->n * g->KP;
+    pad_copy_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(W, g->n, g->k, g->k, 0, g->Wp, g->KP);
+    e = g->d * g->KP;
+    pad_copy_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(T, g->d, g->k, g->d, 1, g->Tp, g->KP);
+}
+
+template <int MODE>
+static int launch_mode(WrriTc* g, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm, int t, float* numer_part,
+                       float* denom_part, int groups, cudaStream_t st, std::string& err)
+{
+    TcParams p;
+    p.X = X; p.ldx = ldx; p.M = M; p.ldm = ldm; p.Wp = g->Wp; p.Tp = g->Tp; p.n = g->n; p.d = g->d; p.KP = g->KP; p.t = t;
+    p.tiles_r = (int)((g->n + TM - 1) / TM); p.tiles_c = (int)((g->d + TN - 1) / TN);
+    p.groups = groups; p.numer_part = numer_part; p.denom_part = denom_part; p.stages = g->stages;
+    dim3 grid(MODE == 0 ? p.tiles_c : p.tiles_r, groups);
+    if (mk == MK_U8) {
+        if (ldm % 4 != 0) { err = "u8 masks need a row stride that is a multiple of 4"; return -1; }
+        auto kern = wrri_tc_kernel<MODE, MK_U8>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+        kern<<<grid, THREADS, g->smem, st>>>(g->tmW, g->tmT, p);
+    } else if (mk == MK_REAL) {
+        if (ldm % 4 != 0) { err = "weights need a row stride that is a multiple of 4"; return -1; }
+        auto kern = wrri_tc_kernel<MODE, MK_REAL>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
+        kern<<<grid, THREADS, g->smem, st>>>(g->tmW, g->tmT, p);
+    } else {
+        err = "the tensor-core WRRI path needs a mask";
+        return -1;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = cudaGetErrorString(e); return -1; }
+    return 1;
+}
+
+int wrri_tc_stats(WrriTc* g, int mode, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm, int t,
+                  float* numer_part, float* denom_part, int groups, cudaStream_t st, std::string& err)
+{
+    if ((reinterpret_cast<uintptr_t>(X) & 15) != 0 || ldx % 4 != 0) { err = "X rows must be 16-byte aligned"; return -1; }
+    return mode == 0 ? launch_mode<0>(g, X, ldx, M, mk, ldm, t, numer_part, denom_part, groups, st, err)
+                     : launch_mode<1>(g, X, ldx, M, mk, ldm, t, numer_part, denom_part, groups, st, err);
+}
+
+}  // namespace rri

@@ -154,6 +154,30 @@ def test_masked_fp32_relerr(R):
     assert abs(re_o - re_g) < F32_RELERR_TOL
 
 
+@pytest.mark.parametrize('order', ['rri', 'hals'])
+@pytest.mark.parametrize('mask_kind', ['u8', 'real'])
+def test_masked_tensor_core_path(R, order, mask_kind):
+    """fp32 + math='tf32' with a mask: the W T tiles come from tcgen05; same 1e-4 criterion, and the
+    TF32 result stays close to the IEEE fp32 kernels on the same inputs."""
+    n, d, k = 700, 520, 13
+    X, W0, T0, M = orc.synth(n, d, k, k, sigma=0.05, seed=23, mask_density=0.15)
+    if mask_kind == 'real':
+        Mw = M * (0.5 + np.random.RandomState(3).rand(n, d))
+        Mg = Mw.astype(np.float32)
+    else:
+        Mw = M
+        Mg = torch.from_numpy(M.astype(np.uint8))
+    o = orc.nmf_oracle(X, k, W0, T0, max_iter=6, W_mat=Mw, order=order, t_row_sum=1.0)
+    kw = dict(max_iter=6, W_mat=Mg, update_order=order, t_row_sum=1.0)
+    g = run(R, X.astype(np.float32), k, W0.astype(np.float32), T0.astype(np.float32), math='tf32', **kw)
+    gi = run(R, X.astype(np.float32), k, W0.astype(np.float32), T0.astype(np.float32), math='ieee', **kw)
+    re_o = orc.rel_error(X, o['W'], o['T'], Mw)
+    re_g = orc.rel_error(X, g['W'].astype(np.float64), g['T'].astype(np.float64), Mw)
+    assert abs(re_o - re_g) < F32_RELERR_TOL, (re_o, re_g)
+    assert relfro(g['W'], gi['W']) < 2e-2 and relfro(g['T'], gi['T']) < 2e-2
+    assert g['T'].max() <= 1.0
+
+
 # ---------------------------------------------------------------------- topic-model setting (f1)
 def test_text_topic_model_simplex(R):
     g = golden('text_tm_f64.npz')
