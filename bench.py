@@ -223,6 +223,7 @@ def main_ours(args):
     X, W0, T0 = gen_shard(torch, cfg, e - b, b, device, seed=rank)
     eng = R.RRIEngine(X, k, order=args.order, math=math, comm=comm)
     params = eng.params()
+    peer_x = bool(getattr(eng, 'peer_exchange', False))
     W, T = W0.clone(), T0.clone()
 
     def barrier():
@@ -285,7 +286,7 @@ def main_ours(args):
             Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
             Xh.copy_(X)
             Wh, Th = W0.cpu().pin_memory(), T0.cpu().pin_memory()
-            del eng
+            eng.close()
             torch.cuda.synchronize()
             s_e2e = args.steps
             barrier()
@@ -323,7 +324,8 @@ def main_ours(args):
                                    % (args.config, n, d, cfg['sigma'], k, cfg['dtype'], world),
                        'update_order': args.order, 'math': math, 'rows_per_gpu': e - b,
                        'l2_policy': 'inputs (%.1f GB/GPU) larger than L2; no flush needed' % (alg_bytes / 1e9),
-                       'final_rel_error': relerr},
+                       'final_rel_error': relerr,
+                       'exchange': ('nvlink peer memory (fused into the T update)' if peer_x else 'nccl all-reduce') if world > 1 else 'none'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         }
         print(json.dumps(line))

@@ -71,6 +71,15 @@ int rri_nccl_comm_create(void** comm_out, const char id[128], int32_t rank, int3
                          const char* nccl_lib_path);
 int rri_nccl_comm_destroy(void* comm);
 
+/* Peer-memory exchange for the block-order T half-step (optional; replaces the NCCL all-reduce of
+ * [X_i'W_i | W_i'W_i] by in-place NVLink reads inside the update kernel).  After rri_bind every rank calls
+ * rri_peer_export (64-byte CUDA IPC handle of its exchange buffer), the host all-gathers the handles
+ * (rank-major, 64 bytes each) and every rank calls rri_peer_import.  Unmasked hals handles only. */
+int rri_peer_export(rri_handle_t h, char handle_out[64]);
+int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank, int32_t world);
+/* switch the exchange on once EVERY rank has imported successfully (the host checks); off = NCCL path */
+int rri_peer_enable(rri_handle_t h, int32_t on);
+
 /* Bind the data (and optional elementwise weights W_mat) resident in device memory.  In hals order
  * the engine builds its own transposed copy of X (one extra pass, once).  nmf.py:98 (X, W_mat). */
 int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX,

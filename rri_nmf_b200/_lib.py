@@ -34,6 +34,9 @@ SYMBOLS = {
     'rri_nccl_unique_id': (C.c_int, [C.c_char * 128, _cp]),
     'rri_nccl_comm_create': (C.c_int, [C.POINTER(_vp), C.c_char * 128, _i32, _i32, _i32, _cp]),
     'rri_nccl_comm_destroy': (C.c_int, [_vp]),
+    'rri_peer_export': (C.c_int, [_vp, C.c_char * 64]),
+    'rri_peer_import': (C.c_int, [_vp, _cp, _i32, _i32]),
+    'rri_peer_enable': (C.c_int, [_vp, _i32]),
     'rri_bind': (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp]),
     'rri_sweeps': (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(RriParams), C.POINTER(_i32), _vp]),
     'rri_topics': (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.POINTER(RriParams), C.POINTER(_i32), _vp]),

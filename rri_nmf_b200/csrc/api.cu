@@ -110,6 +110,16 @@ struct rri_handle_s {
     const void* M = nullptr; int mk = 0; int64_t ldm = 0;
     // comm
     void* comm = nullptr; int rank = 0, world = 1;
+    // peer-memory exchange of the T half-step statistic (multi-GPU hals): every rank exports one buffer
+    //   [2 epochs][d*k + k*k] elements + flag word; all ranks map all buffers (CUDA IPC)
+    void* xbuf = nullptr; size_t xbuf_bytes = 0, xslot_elems = 0;
+    void* peer_base[16] = {nullptr}; bool peer_open[16] = {false};
+    void** d_peerC = nullptr;      // device [2][world] pointers to the C slices
+    void** d_peerG = nullptr;      // device [2][world] pointers to the Gram slices
+    unsigned** d_peerFlag = nullptr;   // device [world] pointers to the epoch flags
+    unsigned epoch = 0;
+    bool p2p = false;
+    int* p2p_err = nullptr;
     // workspace
     std::vector<void*> allocs;
     int64_t ws_bytes = 0, launches = 0;
@@ -181,6 +191,9 @@ extern "C" int rri_destroy(rri_handle_t h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    for (int r = 0; r < 16; ++r)
+        if (h->peer_open[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    if (h->xbuf) cudaFree(h->xbuf);
     for (void* p : h->allocs) cudaFree(p);
     if (h->tf32) tf32_gemm_destroy(h->tf32);
     if (h->wtc) wrri_tc_destroy(h->wtc);
@@ -196,6 +209,103 @@ extern "C" int rri_set_comm(rri_handle_t h, void* nccl_comm, int32_t rank, int32
         if (nccl_load(nccl_lib_path)) return 1;
     }
     h->comm = nccl_comm; h->rank = rank; h->world = world;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// peer-memory exchange (fused replacement of the NCCL all-reduce in the block-order T half-step)
+// -------------------------------------------------------------------------------------------------
+__global__ void peer_signal_kernel(unsigned* flag, unsigned epoch)
+{
+    // everything this rank wrote into its exchange slot (previous kernels of this stream) is made visible
+    // system-wide before the epoch flag is published
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
+__global__ void peer_wait_kernel(unsigned* const* flags, int world, unsigned epoch, int* err)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        const unsigned* f = flags[r];
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (clock64() - t0 > 200000000000LL) {     // ~100 s: a lost peer must not hang the GPU for ever
+                atomicExch(err, 1 + r);
+                __trap();
+            }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
+
+extern "C" int rri_peer_export(rri_handle_t h, char handle_out[64])
+{
+    if (!h) return fail("null handle");
+    if (!h->X) return fail("rri_bind has not been called");
+    if (h->order != RRI_ORDER_HALS || h->mk != MK_NONE) return fail("the peer-memory exchange serves unmasked hals handles");
+    CK(cudaSetDevice(h->device));
+    if (!h->xbuf) {
+        h->xslot_elems = ((size_t)h->d * h->k + (size_t)h->k * h->k + 63) / 64 * 64;
+        h->xbuf_bytes = 2 * h->xslot_elems * h->es + 256;
+        CK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
+        CK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->xbuf));
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle_out, &mh, 64);
+    return 0;
+}
+
+extern "C" int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank, int32_t world)
+{
+    if (!h) return fail("null handle");
+    if (!h->xbuf) return fail("rri_peer_export must be called first");
+    if (world < 2 || world > 16 || rank < 0 || rank >= world) return fail("bad rank/world %d/%d", rank, world);
+    CK(cudaSetDevice(h->device));
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { h->peer_base[r] = h->xbuf; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + 64 * r, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail("cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+        h->peer_base[r] = p; h->peer_open[r] = true;
+    }
+    std::vector<void*> pc(2 * world), pg(2 * world);
+    std::vector<unsigned*> pf(world);
+    for (int r = 0; r < world; ++r) {
+        char* base = (char*)h->peer_base[r];
+        for (int b = 0; b < 2; ++b) {
+            pc[b * world + r] = base + (size_t)b * h->xslot_elems * h->es;
+            pg[b * world + r] = base + ((size_t)b * h->xslot_elems + (size_t)h->d * h->k) * h->es;
+        }
+        pf[r] = (unsigned*)(base + 2 * h->xslot_elems * h->es);
+    }
+    if (ws_alloc(h, (void**)&h->d_peerC, sizeof(void*) * 2 * world) || ws_alloc(h, (void**)&h->d_peerG, sizeof(void*) * 2 * world) ||
+        ws_alloc(h, (void**)&h->d_peerFlag, sizeof(void*) * world) || ws_alloc(h, (void**)&h->p2p_err, sizeof(int)))
+        return 1;
+    CK(cudaMemcpy(h->d_peerC, pc.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_peerG, pg.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_peerFlag, pf.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
+    h->rank = rank; h->world = world; h->epoch = 0; h->p2p = false;     // enabled by rri_peer_enable on ALL ranks
+    return 0;
+}
+
+extern "C" int rri_peer_enable(rri_handle_t h, int32_t on)
+{
+    if (!h) return fail("null handle");
+    if (on && !h->d_peerC) return fail("rri_peer_import has not succeeded on this rank");
+    h->p2p = on != 0;
     return 0;
 }
 
@@ -446,7 +556,7 @@ static int hals_W_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, bool 
         if (contraction<T>(h, (const T*)h->X, h->ldx, Tm, d, (T*)h->Cpart, n, k, d, h->splits_w, st)) return 1;
     }
     const int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_w;
-    launch_update_rows<T>(W, n, k, (const T*)h->Cpart, parts, n * k, (const T*)h->Hm, solve_args(p, false),
+    launch_update_rows<T>(W, n, k, (const T*)h->Cpart, parts, n * k, nullptr, (const T*)h->Hm, solve_args(p, false),
                           (T*)h->Wt, h->ldwt, (T*)h->colsum_part, h->flags, h->ub_blocks_w, st);
     launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_w, k, h->sums, k, h->world > 1 ? 0 : 2, h->flags, st);
     h->launches += 2;
@@ -467,6 +577,31 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
     const int64_t n = h->n, d = h->d;
     T* cg = (T*)h->cg;                 // [d*k | k*k]: X'W partial followed by W'W partial, all-reduced together
     T* G = cg + (size_t)d * k;
+    if (h->world > 1 && h->p2p) {
+        // Fused exchange over NVLink peer memory: this rank's partials [X_i'W_i | W_i'W_i] are produced straight
+        // into its exported slot; after a flag handshake every rank's update kernel reads all slots in place
+        // and adds them in rank order (bit-identical T on all ranks, no separate all-reduce launch).
+        const unsigned e = ++h->epoch;
+        const int b = (int)(e & 1u);
+        T* myC = (T*)((char*)h->xbuf + (size_t)b * h->xslot_elems * h->es);
+        T* myG = myC + (size_t)d * k;
+        launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, myG, st);
+        h->launches += 2;
+        const int psplits = h->math == RRI_MATH_TF32 ? 1 : h->splits_t;
+        T* Cdst = psplits == 1 ? myC : (T*)h->Cpart;
+        if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, Cdst, d, k, n, h->splits_t, st)) return 1;
+        if (psplits > 1) { launch_reduce_parts<T>((const T*)h->Cpart, psplits, d * k, d * k, myC, st); h->launches++; }
+        unsigned* myflag = (unsigned*)((char*)h->xbuf + 2 * h->xslot_elems * h->es);
+        peer_signal_kernel<<<1, 1, 0, st>>>(myflag, e);
+        peer_wait_kernel<<<1, 32, 0, st>>>(h->d_peerFlag, h->world, e, h->p2p_err);
+        launch_sum_sources<T>((const T* const*)(h->d_peerG + (size_t)b * h->world), h->world, (int64_t)k * k, G, st);
+        launch_update_rows<T>((T*)h->Tt, d, k, nullptr, h->world, 0, (const T* const*)(h->d_peerC + (size_t)b * h->world), G,
+                              solve_args(p, true), Tm, d, (T*)h->colsum_part, h->flags, h->ub_blocks_t, st);
+        launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_t, k, h->sums, 0, 1, h->flags, st);
+        h->launches += 5;
+        CKL();
+        return 0;
+    }
     launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, G, st);
     h->launches += 2;
     if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
@@ -479,7 +614,7 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
         C = cg; parts = 1;
     }
     // Tt (d x k) is updated in place; its transpose is written straight into the caller's T (k x d)
-    launch_update_rows<T>((T*)h->Tt, d, k, C, parts, d * k, G, solve_args(p, true), Tm, d, (T*)h->colsum_part,
+    launch_update_rows<T>((T*)h->Tt, d, k, C, parts, d * k, nullptr, G, solve_args(p, true), Tm, d, (T*)h->colsum_part,
                           h->flags, h->ub_blocks_t, st);
     launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_t, k, h->sums, 0, 1, h->flags, st);
     h->launches += 2;

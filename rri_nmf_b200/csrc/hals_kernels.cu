@@ -122,7 +122,7 @@ int update_rows_blocks(int64_t m, int sm_count)
 template <typename T, int KL, bool S_SMEM>
 __global__ void __launch_bounds__(U_THREADS)
 update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cpart, int parts,
-                   int64_t part_stride, const T* __restrict__ S,
+                   int64_t part_stride, const T* const* __restrict__ srcs, const T* __restrict__ S,
                    T reg_l1, T reg_l2, T eps, T ub, int has_ub,
                    T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags)
 {
@@ -158,7 +158,8 @@ update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cp
                     if (tp < k) {
                         f[l] = F[i * k + tp];
                         T c = T(0);
-                        for (int p = 0; p < parts; ++p) c += Cpart[(int64_t)p * part_stride + i * k + tp];
+                        for (int p = 0; p < parts; ++p)
+                            c += (srcs ? srcs[p] : Cpart + (int64_t)p * part_stride)[i * k + tp];
                         r[l] = c;
                     }
                 }
@@ -234,7 +235,7 @@ update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cp
 
 template <typename T, int KL>
 static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
-                                  const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
+                                  const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
                                   int* flags, int blocks, cudaStream_t st)
 {
     size_t base = sizeof(T) * ((size_t)k * (U_GROUP + 1) + (size_t)U_NW * k);
@@ -242,13 +243,13 @@ static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int pa
     if (with_s <= 200 * 1024) {
         auto kern = update_rows_kernel<T, KL, true>;
         if (with_s > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_s);
-        kern<<<blocks, U_THREADS, with_s, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1,
+        kern<<<blocks, U_THREADS, with_s, st>>>(F, m, k, Cpart, parts, part_stride, srcs, S, (T)a.reg_l1,
                                                  (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft,
                                                  colsum_part, flags);
     } else {
         auto kern = update_rows_kernel<T, KL, false>;
         if (base > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
-        kern<<<blocks, U_THREADS, base, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1,
+        kern<<<blocks, U_THREADS, base, st>>>(F, m, k, Cpart, parts, part_stride, srcs, S, (T)a.reg_l1,
                                                (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft,
                                                colsum_part, flags);
     }
@@ -267,7 +268,7 @@ constexpr int TPR_ROWS = 128;       // rows (= threads) per block
 template <typename T, int KM>
 __global__ void __launch_bounds__(TPR_ROWS)
 update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cpart, int parts,
-                       int64_t part_stride, const T* __restrict__ S,
+                       int64_t part_stride, const T* const* __restrict__ srcs, const T* __restrict__ S,
                        T reg_l1, T reg_l2, T eps, T ub, int has_ub,
                        T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags)
 {
@@ -297,7 +298,7 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
             int rr = tid / k, cc = tid - rr * k;
             const int dr = TPR_ROWS / k, dc = TPR_ROWS - dr * k;
             const T* Frow = F + i0 * k;
-            const T* Crow = Cpart + i0 * k;
+            const T* Crow = (srcs ? srcs[0] : Cpart) + i0 * k;
             constexpr int UB = 8;
             for (int e0 = tid; e0 < tot; e0 += UB * TPR_ROWS) {
                 T cv[UB], fv[UB];
@@ -311,10 +312,11 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
                     }
                 }
                 for (int p = 1; p < parts; ++p) {
+                    const T* Cp = srcs ? srcs[p] + i0 * k : Crow + (int64_t)p * part_stride;
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         const int e = e0 + u * TPR_ROWS;
-                        if (e < tot) cv[u] += Crow[(int64_t)p * part_stride + e];
+                        if (e < tot) cv[u] += Cp[e];
                     }
                 }
 #pragma unroll
@@ -387,34 +389,34 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
 
 template <typename T, int KM>
 static void launch_update_rows_tpr(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
-                                   const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
+                                   const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
                                    int* flags, int blocks, cudaStream_t st)
 {
     const size_t smem = sizeof(T) * ((size_t)KM * KM + 2 * (size_t)TPR_ROWS * (KM + 1));
     auto kern = update_rows_tpr_kernel<T, KM>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<blocks, TPR_ROWS, smem, st>>>(F, m, k, Cpart, parts, part_stride, S, (T)a.reg_l1, (T)a.reg_l2,
+    kern<<<blocks, TPR_ROWS, smem, st>>>(F, m, k, Cpart, parts, part_stride, srcs, S, (T)a.reg_l1, (T)a.reg_l2,
                                         (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft, colsum_part, flags);
 }
 
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
-                        const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part, int* flags,
-                        int blocks, cudaStream_t st)
+                        const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft,
+                        T* colsum_part, int* flags, int blocks, cudaStream_t st)
 {
     // thread-per-row variants while the row fits in registers / the tiles in shared memory
     // (fp32: k <= 128, fp64: k <= 64); wider ranks use the warp-per-row kernel
-#define RRI_TPR(KM) launch_update_rows_tpr<T, KM>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st)
+#define RRI_TPR(KM) launch_update_rows_tpr<T, KM>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st)
     if (k <= 16) { RRI_TPR(16); return; }
     if (k <= 32) { RRI_TPR(32); return; }
     if (k <= 64) { RRI_TPR(64); return; }
     if (k <= 128 && sizeof(T) == 4) { RRI_TPR(128); return; }
 #undef RRI_TPR
     const int kl = (k + 31) / 32;
-    if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
-    else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
-    else if (kl <= 4) launch_update_rows_kl<T, 4>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
-    else launch_update_rows_kl<T, 8>(F, m, k, Cpart, parts, part_stride, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    else if (kl <= 4) launch_update_rows_kl<T, 4>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    else launch_update_rows_kl<T, 8>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -516,6 +518,23 @@ void launch_reduce_parts(const T* part, int parts, int64_t stride, int64_t len, 
 }
 
 template <typename T>
+__global__ void sum_sources_kernel(const T* const* __restrict__ srcs, int parts, int64_t len, T* __restrict__ out)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < len) {
+        T s = T(0);
+        for (int p = 0; p < parts; ++p) s += srcs[p][c];
+        out[c] = s;
+    }
+}
+
+template <typename T>
+void launch_sum_sources(const T* const* srcs, int parts, int64_t len, T* out, cudaStream_t st)
+{
+    sum_sources_kernel<T><<<(unsigned)((len + 255) / 256), 256, 0, st>>>(srcs, parts, len, out);
+}
+
+template <typename T>
 void launch_gram(const T* F, int64_t m, int k, T* part, int chunks, T* G, cudaStream_t st)
 {
     const int kb = (k + 63) / 64;
@@ -593,8 +612,10 @@ void launch_transpose(const T* A, int64_t rows, int64_t cols, int64_t lda, T* B,
 #define RRI_INST(T)                                                                                       \
     template void launch_simt_gemm_nt<T>(const T*, int64_t, const T*, int64_t, T*, int64_t, int, int64_t, \
                                          int, cudaStream_t);                                              \
-    template void launch_update_rows<T>(T*, int64_t, int, const T*, int, int64_t, const T*,               \
-                                        const SolveArgs&, T*, int64_t, T*, int*, int, cudaStream_t);      \
+    template void launch_update_rows<T>(T*, int64_t, int, const T*, int, int64_t, const T* const*,        \
+                                        const T*, const SolveArgs&, T*, int64_t, T*, int*, int,            \
+                                        cudaStream_t);                                                     \
+    template void launch_sum_sources<T>(const T* const*, int, int64_t, T*, cudaStream_t);                  \
     template void launch_gram<T>(const T*, int64_t, int, T*, int, T*, cudaStream_t);                      \
     template void launch_reduce_parts<T>(const T*, int, int64_t, int64_t, T*, cudaStream_t);              \
     template void launch_colsum_finalize<T>(const T*, int, int, double*, int, int, int*, cudaStream_t);   \

@@ -71,10 +71,16 @@ void launch_simt_gemm_nt(const T* A, int64_t lda, const T* B, int64_t ldb, T* Cp
 // C = sum of `parts` slices of Cpart.  Writes F in place, optionally Ft[k,m] = F', and per-block
 // column sums colsum_part[blocks][k].   (nmf.py:420-447 / :462-469 applied with the other factor frozen)
 int update_rows_blocks(int64_t m, int sm_count);
+// srcs (optional, device array of `parts` pointers): slice p is srcs[p] instead of Cpart + p*part_stride
+// (the peer-memory all-reduce of the multi-GPU T half-step reads every rank's partial in place).
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
-                        const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part, int* flags,
-                        int blocks, cudaStream_t st);
+                        const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft,
+                        T* colsum_part, int* flags, int blocks, cudaStream_t st);
+
+// out[c] = sum_p srcs[p][c] for c < len (fixed order) -- Gram partials of all ranks read through peer memory
+template <typename T>
+void launch_sum_sources(const T* const* srcs, int parts, int64_t len, T* out, cudaStream_t st);
 
 // Gram matrix G[k,k] = F'F of a row-major F[m,k]: per-chunk partials + fixed-order finalize.
 int gram_chunks(int64_t m, int k, int sm_count);

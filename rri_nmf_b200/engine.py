@@ -2,6 +2,7 @@
 memory.  PyTorch is plumbing only here (allocation, streams, torch.distributed bootstrap): every
 kernel on the sweep path is launched by librri_b200.so."""
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -100,6 +101,28 @@ class RRIEngine(object):
             check(self.lib.rri_set_comm(self.h, comm.comm, comm.rank, comm.world, path))
         check(self.lib.rri_bind(self.h, _ptr(self.X), int(self.X.stride(0)), _ptr(self.W_mat), mk, ldm,
                                 self._stream()))
+        self.peer_exchange = False
+        if (comm is not None and comm.world > 1 and order == 'hals' and self.W_mat is None
+                and os.environ.get('RRI_P2P', '1') != '0'):
+            self._setup_peer_exchange(comm)
+
+    def _setup_peer_exchange(self, comm):
+        """Map every rank's exchange buffer (CUDA IPC over NVLink) so that the T half-step reads the shard
+        statistics of all ranks in place; falls back to the NCCL all-reduce when the mapping is refused."""
+        import torch.distributed as dist
+        hbuf = (C.c_char * 64)()
+        ok = self.lib.rri_peer_export(self.h, hbuf) == 0
+        mine = bytes(hbuf) if ok else b''
+        gathered = [None] * comm.world
+        dist.all_gather_object(gathered, mine)
+        if not all(len(g) == 64 for g in gathered):
+            return
+        rc = self.lib.rri_peer_import(self.h, b''.join(gathered), comm.rank, comm.world)
+        flags = [None] * comm.world
+        dist.all_gather_object(flags, rc == 0)
+        if all(flags):
+            check(self.lib.rri_peer_enable(self.h, 1))
+            self.peer_exchange = True
 
     # ------------------------------------------------------------------------------------------
     def _stream(self):
@@ -107,6 +130,16 @@ class RRIEngine(object):
 
     def close(self):
         if getattr(self, 'h', None):
+            if getattr(self, 'peer_exchange', False):
+                # peers may still be reading this rank's exchange buffer: leave together
+                try:
+                    import torch.distributed as dist
+                    if dist.is_initialized():
+                        torch.cuda.synchronize(self.device)
+                        dist.barrier()
+                except Exception:
+                    pass
+                self.peer_exchange = False
             self.lib.rri_destroy(self.h)
             self.h = C.c_void_p()
 
