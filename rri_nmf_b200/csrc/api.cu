@@ -9,6 +9,7 @@
 
 #include "../../include/rri_b200.h"
 #include "gemm_tf32_sm100.h"
+#include "common.cuh"
 #include "kernels.h"
 #include "wrri_tc_sm100.h"
 
@@ -114,9 +115,9 @@ struct rri_handle_s {
     //   [2 epochs][d*k + k*k] elements + flag word; all ranks map all buffers (CUDA IPC)
     void* xbuf = nullptr; size_t xbuf_bytes = 0, xslot_elems = 0;
     void* peer_base[16] = {nullptr}; bool peer_open[16] = {false};
-    void** d_peerC = nullptr;      // device [2][world] pointers to the C slices
-    void** d_peerG = nullptr;      // device [2][world] pointers to the Gram slices
-    unsigned** d_peerFlag = nullptr;   // device [world] pointers to the epoch flags
+    void** d_peerP = nullptr;      // device [2][world] pointers to the ranks' partial slots  [X_i'W_i | W_i'W_i]
+    void** d_peerR = nullptr;      // device [2][world] pointers to the ranks' reduced slots
+    unsigned** d_peerFlag = nullptr;   // device [2][world] pointers to the two epoch flags of every rank
     unsigned epoch = 0;
     bool p2p = false;
     int* p2p_err = nullptr;
@@ -243,6 +244,44 @@ __global__ void peer_wait_kernel(unsigned* const* flags, int world, unsigned epo
     __threadfence_system();
 }
 
+// Two-shot all-reduce over peer memory.  Rank r owns the r-th slice of the statistic vector: it adds the
+// slice of every rank's partial slot in rank order (7 remote reads) and stores the result into every rank's
+// reduced slot (7 remote writes).  Each rank moves 2*(g-1)/g of the vector over NVLink, like a ring, but in
+// two latency hops; the fixed summation order makes the result bit-identical on all ranks.
+template <typename T>
+__global__ void __launch_bounds__(256)
+peer_reduce_scatter_gather_kernel(T* const* partial, T* const* reduced, int world, int rank, int64_t len)
+{
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    const int64_t nvec = len / VN;                 // len is padded to a multiple of 64 elements
+    const int64_t per = (nvec + world - 1) / world;
+    const int64_t lo = per * rank, hi = (lo + per) < nvec ? (lo + per) : nvec;
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+        V v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (r < world) v[r] = reinterpret_cast<const V*>(partial[r])[i];
+        T acc[VN];
+        unpack(v[0], acc);
+#pragma unroll
+        for (int r = 1; r < 16; ++r)
+            if (r < world) {
+                T t[VN];
+                unpack(v[r], t);
+#pragma unroll
+                for (int q = 0; q < VN; ++q) acc[q] += t[q];
+            }
+        V out;
+        T* o = reinterpret_cast<T*>(&out);
+#pragma unroll
+        for (int q = 0; q < VN; ++q) o[q] = acc[q];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (r < world) reinterpret_cast<V*>(reduced[r])[i] = out;
+    }
+}
+
 extern "C" int rri_peer_export(rri_handle_t h, char handle_out[64])
 {
     if (!h) return fail("null handle");
@@ -251,7 +290,7 @@ extern "C" int rri_peer_export(rri_handle_t h, char handle_out[64])
     CK(cudaSetDevice(h->device));
     if (!h->xbuf) {
         h->xslot_elems = ((size_t)h->d * h->k + (size_t)h->k * h->k + 63) / 64 * 64;
-        h->xbuf_bytes = 2 * h->xslot_elems * h->es + 256;
+        h->xbuf_bytes = 4 * h->xslot_elems * h->es + 256;
         CK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
         CK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
         CK(cudaDeviceSynchronize());
@@ -281,22 +320,22 @@ extern "C" int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank
         }
         h->peer_base[r] = p; h->peer_open[r] = true;
     }
-    std::vector<void*> pc(2 * world), pg(2 * world);
-    std::vector<unsigned*> pf(world);
+    std::vector<void*> pp(2 * world), pr(2 * world);
+    std::vector<unsigned*> pf(2 * world);
     for (int r = 0; r < world; ++r) {
         char* base = (char*)h->peer_base[r];
         for (int b = 0; b < 2; ++b) {
-            pc[b * world + r] = base + (size_t)b * h->xslot_elems * h->es;
-            pg[b * world + r] = base + ((size_t)b * h->xslot_elems + (size_t)h->d * h->k) * h->es;
+            pp[b * world + r] = base + (size_t)(2 * b) * h->xslot_elems * h->es;
+            pr[b * world + r] = base + (size_t)(2 * b + 1) * h->xslot_elems * h->es;
+            pf[b * world + r] = (unsigned*)(base + 4 * h->xslot_elems * h->es) + 32 * b;    // 128 bytes apart
         }
-        pf[r] = (unsigned*)(base + 2 * h->xslot_elems * h->es);
     }
-    if (ws_alloc(h, (void**)&h->d_peerC, sizeof(void*) * 2 * world) || ws_alloc(h, (void**)&h->d_peerG, sizeof(void*) * 2 * world) ||
-        ws_alloc(h, (void**)&h->d_peerFlag, sizeof(void*) * world) || ws_alloc(h, (void**)&h->p2p_err, sizeof(int)))
+    if (ws_alloc(h, (void**)&h->d_peerP, sizeof(void*) * 2 * world) || ws_alloc(h, (void**)&h->d_peerR, sizeof(void*) * 2 * world) ||
+        ws_alloc(h, (void**)&h->d_peerFlag, sizeof(void*) * 2 * world) || ws_alloc(h, (void**)&h->p2p_err, sizeof(int)))
         return 1;
-    CK(cudaMemcpy(h->d_peerC, pc.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_peerG, pg.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_peerFlag, pf.data(), sizeof(void*) * world, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_peerP, pp.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_peerR, pr.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_peerFlag, pf.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
     h->rank = rank; h->world = world; h->epoch = 0; h->p2p = false;     // enabled by rri_peer_enable on ALL ranks
     return 0;
 }
@@ -304,7 +343,7 @@ extern "C" int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank
 extern "C" int rri_peer_enable(rri_handle_t h, int32_t on)
 {
     if (!h) return fail("null handle");
-    if (on && !h->d_peerC) return fail("rri_peer_import has not succeeded on this rank");
+    if (on && !h->d_peerP) return fail("rri_peer_import has not succeeded on this rank");
     h->p2p = on != 0;
     return 0;
 }
@@ -583,22 +622,32 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
         // and adds them in rank order (bit-identical T on all ranks, no separate all-reduce launch).
         const unsigned e = ++h->epoch;
         const int b = (int)(e & 1u);
-        T* myC = (T*)((char*)h->xbuf + (size_t)b * h->xslot_elems * h->es);
+        char* slot = (char*)h->xbuf + (size_t)(2 * b) * h->xslot_elems * h->es;
+        T* myC = (T*)slot;                                   // partial  [d*k | k*k]
         T* myG = myC + (size_t)d * k;
+        T* redC = (T*)(slot + h->xslot_elems * h->es);       // reduced  [d*k | k*k], filled by the slice owners
+        T* redG = redC + (size_t)d * k;
         launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, myG, st);
         h->launches += 2;
         const int psplits = h->math == RRI_MATH_TF32 ? 1 : h->splits_t;
         T* Cdst = psplits == 1 ? myC : (T*)h->Cpart;
         if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, Cdst, d, k, n, h->splits_t, st)) return 1;
         if (psplits > 1) { launch_reduce_parts<T>((const T*)h->Cpart, psplits, d * k, d * k, myC, st); h->launches++; }
-        unsigned* myflag = (unsigned*)((char*)h->xbuf + 2 * h->xslot_elems * h->es);
-        peer_signal_kernel<<<1, 1, 0, st>>>(myflag, e);
+        unsigned* myflags = (unsigned*)((char*)h->xbuf + 4 * h->xslot_elems * h->es);
+        const int64_t len = (int64_t)h->xslot_elems;
+        int rblocks = (int)((len / (16 / (int64_t)h->es) / h->world + 255) / 256);
+        if (rblocks > 4 * h->sm_count) rblocks = 4 * h->sm_count;
+        if (rblocks < 1) rblocks = 1;
+        peer_signal_kernel<<<1, 1, 0, st>>>(myflags, e);                                   // partial published
         peer_wait_kernel<<<1, 32, 0, st>>>(h->d_peerFlag, h->world, e, h->p2p_err);
-        launch_sum_sources<T>((const T* const*)(h->d_peerG + (size_t)b * h->world), h->world, (int64_t)k * k, G, st);
-        launch_update_rows<T>((T*)h->Tt, d, k, nullptr, h->world, 0, (const T* const*)(h->d_peerC + (size_t)b * h->world), G,
-                              solve_args(p, true), Tm, d, (T*)h->colsum_part, h->flags, h->ub_blocks_t, st);
+        peer_reduce_scatter_gather_kernel<T><<<rblocks, 256, 0, st>>>((T* const*)(h->d_peerP + (size_t)b * h->world),
+                                                                       (T* const*)(h->d_peerR + (size_t)b * h->world), h->world, h->rank, len);
+        peer_signal_kernel<<<1, 1, 0, st>>>(myflags + 32, e);                              // my slice stored everywhere
+        peer_wait_kernel<<<1, 32, 0, st>>>(h->d_peerFlag + h->world, h->world, e, h->p2p_err);
+        launch_update_rows<T>((T*)h->Tt, d, k, redC, 1, d * k, nullptr, redG, solve_args(p, true), Tm, d,
+                              (T*)h->colsum_part, h->flags, h->ub_blocks_t, st);
         launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_t, k, h->sums, 0, 1, h->flags, st);
-        h->launches += 5;
+        h->launches += 7;
         CKL();
         return 0;
     }
