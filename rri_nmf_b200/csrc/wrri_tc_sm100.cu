@@ -10,7 +10,7 @@
 // epilogue warps move it to shared memory and then walk X and the mask in their own row-major,
 // fully coalesced order, adding topic t back in fp32 (W_{t->0}T = WT - w_t T_t).  With a sparse
 // mask the X loads of all-masked 16-byte groups are skipped, so the pass reads the mask once and only
-// the observed neighbourhood of X.
+// the observed neighbourhood of X.  Tiles are 128x64 so that two CTAs share an SM.
 //
 // Operands are engine-owned zero-padded copies Wp[n, KP], Tp[d, KP] (K-contiguous rows of KP = k
 // rounded up to 32 floats -> legal TMA rows and whole 128-byte swizzle atoms).
@@ -25,13 +25,16 @@ namespace rri {
 
 namespace {
 
-constexpr int TM = 128, TN = 128;          // tile: rows of X x columns of X
+constexpr int TM = 128, TN = 64;           // tile: rows of X x columns of X (two CTAs per SM: a second tile
+                                           // is in flight while this one waits on its loads)
 constexpr int BK = 32;                     // floats per 128-byte swizzle row
 constexpr int UK = 8;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (1 + EPI_WARPS);
 constexpr int DS_LD = TN + 4;              // padded row stride of the staged product tile (floats)
-constexpr int OP_CHUNK_BYTES = TM * BK * 4;   // one 32-float K chunk of a 128-row operand tile: 16 KB
+constexpr int W_CHUNK_BYTES = TM * BK * 4;    // one 32-float K chunk of the 128-row W tile: 16 KB
+constexpr int T_CHUNK_BYTES = TN * BK * 4;    // one 32-float K chunk of the  64-row T' tile:  8 KB
+constexpr int ROWS_PER_THREAD = 8;            // element-wise pass: 128x64 tile / 256 threads / 4 columns
 
 struct TcParams {
     const float* X; int64_t ldx;
@@ -147,19 +150,24 @@ template <> struct MaskRaw<MK_REAL> {
     __device__ __forceinline__ void decode(float m[4]) const { m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w; }
 };
 
-// MODE 0: T-step statistics (column sums; CTA = one column tile x one row group)
-// MODE 1: W-step statistics (row sums;    CTA = one row tile    x one column group)
+// MODE 0: T-step statistics (column sums; CTA = one 64-column tile x one group of 128-row tiles)
+// MODE 1: W-step statistics (row sums;    CTA = one 128-row tile   x one group of 64-column tiles)
+// 288 threads: warp 0 = TMA + MMA control, warps 1-8 = epilogue.  Two CTAs are resident per SM.
 template <int MODE, int MK>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 2)
 wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT, TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int nchunk = p.KP / BK;
-    const int op_bytes = nchunk * OP_CHUNK_BYTES;           // one 128-row operand tile
+    const int w_bytes = nchunk * W_CHUNK_BYTES, t_bytes = nchunk * T_CHUNK_BYTES;     // W tile 128 rows, T' tile 64 rows
+    const int fixed_bytes = MODE == 0 ? t_bytes : w_bytes;
+    const int var_bytes = MODE == 0 ? w_bytes : t_bytes;
+    const int var_chunk = MODE == 0 ? W_CHUNK_BYTES : T_CHUNK_BYTES;
+    const int fixed_chunk = MODE == 0 ? T_CHUNK_BYTES : W_CHUNK_BYTES;
     uint8_t* sm_fixed = smem;                               // the operand that stays for the whole CTA
-    uint8_t* sm_var = smem + op_bytes;                      // [stages] the operand that changes per tile
-    float* Ds = reinterpret_cast<float*>(sm_var + (size_t)p.stages * op_bytes);     // [TM][DS_LD]
+    uint8_t* sm_var = smem + fixed_bytes;                   // [stages] the operand that changes per tile
+    float* Ds = reinterpret_cast<float*>(sm_var + (size_t)p.stages * var_bytes);      // [TM][DS_LD]
     uint64_t* bars = reinterpret_cast<uint64_t*>(Ds + TM * DS_LD);
     uint64_t* fixed_full = bars;            // 1
     uint64_t* var_full = bars + 1;          // [2]
@@ -169,7 +177,6 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile walk of this CTA
     const int fixed_tile = blockIdx.x;      // column tile (MODE 0) / row tile (MODE 1)
     const int nvar_total = MODE == 0 ? p.tiles_r : p.tiles_c;
     int vb, ve;
@@ -179,6 +186,7 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         ve = vb + q + (g < r ? 1 : 0);
     }
     const int ntiles = ve - vb;
+    const int var_rows = MODE == 0 ? TM : TN, fixed_rows = MODE == 0 ? TN : TM;       // rows per tile of each operand
 
     if (threadIdx.x == 0) {
         mbar_init(fixed_full, 1);
@@ -186,7 +194,7 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -197,32 +205,32 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     if (warp == 0) {
         // ================================ TMA + MMA control thread ================================
         if (lane == 0 && ntiles > 0) {
-            const CUtensorMap* tm_fixed = MODE == 0 ? &tmT : &tmW;     // MODE 0: column tile of T' is fixed
+            const CUtensorMap* tm_fixed = MODE == 0 ? &tmT : &tmW;     // MODE 0: the column tile of T' is fixed
             const CUtensorMap* tm_var = MODE == 0 ? &tmW : &tmT;
-            // A operand = W rows (D lanes = rows of X), B operand = T' rows (D columns = columns of X)
-            mbar_expect_tx(fixed_full, (uint32_t)op_bytes);
-            for (int c = 0; c < nchunk; ++c) tma_load_2d(tm_fixed, sm_fixed + c * OP_CHUNK_BYTES, fixed_full, c * BK, fixed_tile * TM);
+            mbar_expect_tx(fixed_full, (uint32_t)fixed_bytes);
+            for (int c = 0; c < nchunk; ++c) tma_load_2d(tm_fixed, sm_fixed + c * fixed_chunk, fixed_full, c * BK, fixed_tile * fixed_rows);
             const int S = p.stages;
             for (int s0 = 0; s0 < S && s0 < ntiles; ++s0) {           // prologue: fill the ring
-                mbar_expect_tx(&var_full[s0], (uint32_t)op_bytes);
+                mbar_expect_tx(&var_full[s0], (uint32_t)var_bytes);
                 for (int c = 0; c < nchunk; ++c)
-                    tma_load_2d(tm_var, sm_var + (size_t)s0 * op_bytes + c * OP_CHUNK_BYTES, &var_full[s0], c * BK, (vb + s0) * TM);
+                    tma_load_2d(tm_var, sm_var + (size_t)s0 * var_bytes + c * var_chunk, &var_full[s0], c * BK, (vb + s0) * var_rows);
             }
             mbar_wait(fixed_full, 0);
+            // D[128 rows of X, 64 columns of X] = W tile (A, M = 128) x T' tile (B, N = 64), TF32 in, FP32 out
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             for (int n = 0; n < ntiles; ++n) {
                 const int s = n % S, a = n & 1;
                 mbar_wait(&var_full[s], (n / S) & 1);
                 mbar_wait(&acc_free[a], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t var0 = smem_u32(sm_var + (size_t)s * op_bytes), fix0 = smem_u32(sm_fixed);
+                const uint32_t var0 = smem_u32(sm_var + (size_t)s * var_bytes), fix0 = smem_u32(sm_fixed);
                 const uint32_t w0 = MODE == 0 ? var0 : fix0;      // W tile (A)
                 const uint32_t t0 = MODE == 0 ? fix0 : var0;      // T' tile (B)
                 for (int c = 0; c < nchunk; ++c) {
 #pragma unroll
                     for (int ks = 0; ks < BK / UK; ++ks) {
-                        umma_tf32(tmem_base + (uint32_t)(a * TN), make_desc(w0 + c * OP_CHUNK_BYTES + ks * UK * 4),
-                                  make_desc(t0 + c * OP_CHUNK_BYTES + ks * UK * 4), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base + (uint32_t)(a * TN), make_desc(w0 + c * W_CHUNK_BYTES + ks * UK * 4),
+                                  make_desc(t0 + c * T_CHUNK_BYTES + ks * UK * 4), idesc, (c > 0 || ks > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&var_free[s]);
@@ -230,9 +238,9 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                 if (n + S < ntiles) {
                     // refill this stage for tile n+S once the MMAs that read it have retired
                     mbar_wait(&var_free[s], (n / S) & 1);
-                    mbar_expect_tx(&var_full[s], (uint32_t)op_bytes);
+                    mbar_expect_tx(&var_full[s], (uint32_t)var_bytes);
                     for (int c = 0; c < nchunk; ++c)
-                        tma_load_2d(tm_var, sm_var + (size_t)s * op_bytes + c * OP_CHUNK_BYTES, &var_full[s], c * BK, (vb + n + S) * TM);
+                        tma_load_2d(tm_var, sm_var + (size_t)s * var_bytes + c * var_chunk, &var_full[s], c * BK, (vb + n + S) * var_rows);
                 }
             }
         }
@@ -240,11 +248,14 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         // ======================================= epilogue ========================================
         const int ew = warp - 1;                 // 0..7
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        // coalesced element-wise mapping: lane owns 4 consecutive columns, warp ew owns rows ew, ew+8, ...
-        const int cl = 4 * lane;
-        float nacc[MODE == 0 ? 4 : 16], dacc[MODE == 0 ? 4 : 16];
+        // coalesced element-wise mapping: 16 lanes x 4 columns cover the 64 columns of a row; a warp takes
+        // two rows per step, warp ew owns rows 2*ew + (lane >> 4) + 16*rr
+        constexpr int R = ROWS_PER_THREAD;
+        const int cl = 4 * (lane & 15);
+        const int rsub = 2 * ew + (lane >> 4);
+        float nacc[MODE == 0 ? 4 : R], dacc[MODE == 0 ? 4 : R];
 #pragma unroll
-        for (int i = 0; i < (MODE == 0 ? 4 : 16); ++i) { nacc[i] = 0.f; dacc[i] = 0.f; }
+        for (int i = 0; i < (MODE == 0 ? 4 : R); ++i) { nacc[i] = 0.f; dacc[i] = 0.f; }
 
         for (int n = 0; n < ntiles; ++n) {
             const int a = n & 1;
@@ -254,10 +265,10 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const int64_t gc = c0 + cl;
             const bool cok = gc < p.d;                                // d % 4 == 0 is required by the launcher
             // the masks do not depend on the product tile: request them before blocking on the MMA
-            MaskRaw<MK> mr[16];
+            MaskRaw<MK> mr[R];
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-                const int64_t gi = i0 + ew + 8 * rr;
+            for (int rr = 0; rr < R; ++rr) {
+                const int64_t gi = i0 + rsub + 16 * rr;
                 mr[rr].load(p.M, gi * p.ldm + gc, cok && gi < p.n);
             }
             float tt[4] = {0.f, 0.f, 0.f, 0.f};
@@ -267,13 +278,13 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
             mbar_wait(&acc_full[a], (n >> 1) & 1);
             tc_fence_after();
-            {   // TMEM -> shared: the two warps of a lane quarter take 64 columns each
+            {   // TMEM -> shared: the two warps of a lane quarter take 32 columns each
                 const int half = (warp - 1) >> 2;                     // warps 1-4 -> 0, warps 5-8 -> 1
                 const int row = q * 32 + lane;
-#pragma unroll 1
-                for (int cc = 0; cc < 64; cc += 16) {
+#pragma unroll
+                for (int cc = 0; cc < 32; cc += 16) {
                     float v[16];
-                    const int col = half * 64 + cc;
+                    const int col = half * 32 + cc;
                     tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + col), v);
                     float4* o = reinterpret_cast<float4*>(Ds + row * DS_LD + col);
                     o[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -282,13 +293,14 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     o[3] = make_float4(v[12], v[13], v[14], v[15]);
                 }
             }
-            // observed X groups of this tile: all 16 rows' loads in flight together (one round trip), issued
-            // before the barrier so that part of their latency hides behind it
-            float4 xv[16];
-            float wts[16];
+            // observed X groups of this tile: all rows' loads in flight together (one round trip), issued
+            // before the barrier so that part of their latency hides behind it.  (Loading X unconditionally,
+            // without waiting for the mask, was measured slower: 0.54 s vs 0.40 s per config-4 sweep.)
+            float4 xv[R];
+            float wts[R];
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-                const int64_t gi = i0 + ew + 8 * rr;
+            for (int rr = 0; rr < R; ++rr) {
+                const int64_t gi = i0 + rsub + 16 * rr;
                 xv[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
                 wts[rr] = 0.f;
                 if (mr[rr].any()) {
@@ -302,9 +314,9 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
             // ---- element-wise pass in X's own layout
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
+            for (int rr = 0; rr < R; ++rr) {
                 if (mr[rr].any()) {
-                    const int r = ew + 8 * rr;
+                    const int r = rsub + 16 * rr;
                     float m[4];
                     mr[rr].decode(m);
                     const float4 dv = *reinterpret_cast<const float4*>(Ds + r * DS_LD + cl);
@@ -329,30 +341,33 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
         // ---- reductions and partial output
         if (MODE == 0) {
-            // column sums: add the 8 warps through shared memory (Ds is free now)
-            float* red = Ds;                                          // [8][2][128]
+            // column sums: 16 thread rows (8 warps x 2 half-warps) per column, added through shared memory
+            float* red = Ds;                                          // [16][2][TN]
+            const int slot = 2 * ew + (lane >> 4);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                red[(ew * 2 + 0) * TN + cl + v] = nacc[v];
-                red[(ew * 2 + 1) * TN + cl + v] = dacc[v];
+                red[(slot * 2 + 0) * TN + cl + v] = nacc[v];
+                red[(slot * 2 + 1) * TN + cl + v] = dacc[v];
             }
             epi_barrier();
             const int e = threadIdx.x - 32;                           // 0..255
-            const int which = e >> 7, cc = e & 127;
-            float s = 0.f;
+            if (e < 2 * TN) {
+                const int which = e / TN, cc = e % TN;
+                float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < EPI_WARPS; ++w) s += red[(w * 2 + which) * TN + cc];
-            const int64_t gcol = (int64_t)fixed_tile * TN + cc;
-            if (gcol < p.d) (which ? p.denom_part : p.numer_part)[(int64_t)blockIdx.y * p.d + gcol] = s;
+                for (int w = 0; w < 16; ++w) s += red[(w * 2 + which) * TN + cc];
+                const int64_t gcol = (int64_t)fixed_tile * TN + cc;
+                if (gcol < p.d) (which ? p.denom_part : p.numer_part)[(int64_t)blockIdx.y * p.d + gcol] = s;
+            }
         } else {
-            // row sums: lanes hold per-row partials over their column slices
+            // row sums: the 16 lanes that share a row hold partials over their column slices
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
+            for (int rr = 0; rr < R; ++rr) {
                 float a = nacc[rr], b = dacc[rr];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-                const int64_t gi = (int64_t)fixed_tile * TM + ew + 8 * rr;
-                if (lane == 0 && gi < p.n) {
+                for (int o = 8; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                const int64_t gi = (int64_t)fixed_tile * TM + rsub + 16 * rr;
+                if ((lane & 15) == 0 && gi < p.n) {
                     p.numer_part[(int64_t)blockIdx.y * p.n + gi] = a;
                     p.denom_part[(int64_t)blockIdx.y * p.n + gi] = b;
                 }
@@ -363,7 +378,7 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
     }
 }
 
@@ -394,8 +409,8 @@ struct WrriTc {
     float* Wp = nullptr;
     float* Tp = nullptr;
     CUtensorMap tmW, tmT;
-    int stages = 2;
-    size_t smem = 0;
+    int stages[2] = {1, 2};
+    size_t smem[2] = {0, 0};
 };
 
 WrriTc* wrri_tc_create(int sm_count, int64_t n, int64_t d, int k, std::string& err)
@@ -420,23 +435,29 @@ WrriTc* wrri_tc_create(int sm_count, int64_t n, int64_t d, int k, std::string& e
         wrri_tc_destroy(g);
         return nullptr;
     }
-    auto enc = [&](CUtensorMap* tm, float* base, int64_t rows) -> bool {
+    auto enc = [&](CUtensorMap* tm, float* base, int64_t rows, int box_rows) -> bool {
         cuuint64_t gdim[2] = {(cuuint64_t)g->KP, (cuuint64_t)rows};
         cuuint64_t gstr[1] = {(cuuint64_t)g->KP * 4};
-        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)TM};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
         cuuint32_t estr[2] = {1, 1};
         return g->encode(tm, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
-    if (!enc(&g->tmW, g->Wp, n) || !enc(&g->tmT, g->Tp, d)) {
+    if (!enc(&g->tmW, g->Wp, n, TM) || !enc(&g->tmT, g->Tp, d, TN)) {
         err = "cuTensorMapEncodeTiled failed for the WRRI operands";
         wrri_tc_destroy(g);
         return nullptr;
     }
-    const int op_bytes = (g->KP / BK) * OP_CHUNK_BYTES;
-    g->stages = g->KP <= 64 ? 2 : 1;
-    g->smem = (size_t)op_bytes * (1 + g->stages) + sizeof(float) * TM * DS_LD + 256 + 1024;
+    // shared memory per CTA (two CTAs must fit in one SM): fixed operand + ring of the changing operand +
+    // the staged product tile + barriers/alignment
+    const int w_bytes = (g->KP / BK) * W_CHUNK_BYTES, t_bytes = (g->KP / BK) * T_CHUNK_BYTES;
+    const size_t ds = sizeof(float) * TM * DS_LD + 256 + 1024;
+    for (int mode = 0; mode < 2; ++mode) {
+        const int fixed = mode == 0 ? t_bytes : w_bytes, var = mode == 0 ? w_bytes : t_bytes;
+        g->stages[mode] = (fixed + 2 * (size_t)var + ds <= 112 * 1024) ? 2 : 1;
+        g->smem[mode] = (size_t)fixed + (size_t)g->stages[mode] * var + ds;
+    }
     return g;
 }
 
@@ -457,7 +478,7 @@ int wrri_tc_groups(WrriTc* g, int mode)
     const int tiles_r = (int)((g->n + TM - 1) / TM), tiles_c = (int)((g->d + TN - 1) / TN);
     const int fixed = mode == 0 ? tiles_c : tiles_r, var = mode == 0 ? tiles_r : tiles_c;
     // enough CTAs for ~8 waves of one CTA per SM, at least 4 tiles per CTA when there are that many
-    int groups = (8 * g->sm_count + fixed - 1) / fixed;
+    int groups = (16 * g->sm_count + fixed - 1) / fixed;
     if (groups > (var + 3) / 4) groups = (var + 3) / 4;
     if (groups < 1) groups = 1;
     return groups;
@@ -479,18 +500,18 @@ static int launch_mode(WrriTc* g, const float* X, int64_t ldx, const void* M, in
     TcParams p;
     p.X = X; p.ldx = ldx; p.M = M; p.ldm = ldm; p.Wp = g->Wp; p.Tp = g->Tp; p.n = g->n; p.d = g->d; p.KP = g->KP; p.t = t;
     p.tiles_r = (int)((g->n + TM - 1) / TM); p.tiles_c = (int)((g->d + TN - 1) / TN);
-    p.groups = groups; p.numer_part = numer_part; p.denom_part = denom_part; p.stages = g->stages;
+    p.groups = groups; p.numer_part = numer_part; p.denom_part = denom_part; p.stages = g->stages[MODE];
     dim3 grid(MODE == 0 ? p.tiles_c : p.tiles_r, groups);
     if (mk == MK_U8) {
         if (ldm % 4 != 0) { err = "u8 masks need a row stride that is a multiple of 4"; return -1; }
         auto kern = wrri_tc_kernel<MODE, MK_U8>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
-        kern<<<grid, THREADS, g->smem, st>>>(g->tmW, g->tmT, p);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem[MODE]);
+        kern<<<grid, THREADS, g->smem[MODE], st>>>(g->tmW, g->tmT, p);
     } else if (mk == MK_REAL) {
         if (ldm % 4 != 0) { err = "weights need a row stride that is a multiple of 4"; return -1; }
         auto kern = wrri_tc_kernel<MODE, MK_REAL>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem);
-        kern<<<grid, THREADS, g->smem, st>>>(g->tmW, g->tmT, p);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem[MODE]);
+        kern<<<grid, THREADS, g->smem[MODE], st>>>(g->tmW, g->tmT, p);
     } else {
         err = "the tensor-core WRRI path needs a mask";
         return -1;
