@@ -336,25 +336,33 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
 #pragma unroll
         for (int j = 0; j < KM; ++j) f[j] = (j < k && tid < nrow) ? ftile[tid * LD + j] : T(0);
         if (tid < nrow) {
+            // topics in groups of 8: t = 8c + u with u unrolled, so the register holding f[t] can only be one
+            // of the 8 entries f[u], f[u+8], ... -- 8 selects per step instead of KM
 #pragma unroll 1
-            for (int t = 0; t < k; ++t) {
-                const V* srow = reinterpret_cast<const V*>(Ss + t * KM);
-                T acc[4] = {T(0), T(0), T(0), T(0)};
+            for (int c = 0; c < (k + 7) / 8; ++c) {
 #pragma unroll
-                for (int jv = 0; jv < KM / VN; ++jv) {
-                    T sv[VN];
-                    unpack(srow[jv], sv);
+                for (int u = 0; u < 8; ++u) {
+                    const int t = 8 * c + u;
+                    if (t < k) {
+                        const V* srow = reinterpret_cast<const V*>(Ss + t * KM);
+                        T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
-                    for (int v = 0; v < VN; ++v) acc[(jv * VN + v) & 3] = fma(f[jv * VN + v], sv[v], acc[(jv * VN + v) & 3]);
+                        for (int jv = 0; jv < KM / VN; ++jv) {
+                            T sv[VN];
+                            unpack(srow[jv], sv);
+#pragma unroll
+                            for (int v = 0; v < VN; ++v) acc[(jv * VN + v) & 3] = fma(f[jv * VN + v], sv[v], acc[(jv * VN + v) & 3]);
+                        }
+                        const T stt = Ss[t * KM + t];
+                        const T ft = ftile[tid * LD + t];
+                        // sum over j != t: remove the own term from the full dot product
+                        const T dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
+                        const T x = solve_scalar_c<T>(ctile[tid * LD + t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
+                        ftile[tid * LD + t] = x;
+#pragma unroll
+                        for (int jj = 0; jj < KM / 8; ++jj) f[8 * jj + u] = (jj == c) ? x : f[8 * jj + u];
+                    }
                 }
-                const T stt = Ss[t * KM + t];
-                const T ft = ftile[tid * LD + t];
-                // sum over j != t: remove the own term from the full dot product
-                const T dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
-                const T x = solve_scalar_c<T>(ctile[tid * LD + t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
-                ftile[tid * LD + t] = x;
-#pragma unroll
-                for (int j = 0; j < KM; ++j) f[j] = (j == t) ? x : f[j];
             }
         }
         __syncthreads();

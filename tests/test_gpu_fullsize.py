@@ -1,0 +1,61 @@
+"""Size-independent properties at BASELINE.json's full headline size (config 3: 200000 x 20000, k=64, fp32),
+where the CPU oracle cannot go: monotone objective, non-negativity, bitwise run-to-run and re-entrance
+determinism, and agreement of the two arithmetic modes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cfg3(cuda_device):
+    free, _ = torch.cuda.mem_get_info(cuda_device)
+    if free < 60e9:
+        pytest.skip('needs ~40 GB of device memory')
+    import bench
+    cfg = dict(bench.CONFIGS['cfg3'])
+    X, W0, T0 = bench.gen_shard(torch, cfg, cfg['n'], 0, cuda_device, seed=0)
+    yield X, W0, T0
+    del X, W0, T0
+    torch.cuda.empty_cache()
+
+
+def test_full_size_block_order_properties(cfg3):
+    import rri_nmf_b200 as R
+    X, W0, T0 = cfg3
+    eng = R.RRIEngine(X, 64, order='hals', math='tf32')
+    p = eng.params()
+    W, T = W0.clone(), T0.clone()
+    objs = [eng.objective(W, T)]
+    for _ in range(3):
+        assert eng.sweeps(W, T, 1, p) == 0                      # no zero-topic / unbounded / non-finite flags
+        objs.append(eng.objective(W, T))
+    assert np.all(np.diff(objs) < 0), objs                      # reference tests/test_nmf.py:40 at full size
+    assert float(W.min()) >= 0.0 and float(T.min()) >= 0.0
+    assert bool(torch.isfinite(W).all()) and bool(torch.isfinite(T).all())
+    # 3 x 1 sweep == 1 x 3 sweeps, bit for bit, and run-to-run
+    W2, T2 = W0.clone(), T0.clone()
+    eng.sweeps(W2, T2, 3, p)
+    assert torch.equal(W, W2) and torch.equal(T, T2)
+    eng.close()
+
+
+def test_full_size_interleaved_order_properties(cfg3):
+    import rri_nmf_b200 as R
+    X, W0, T0 = cfg3
+    eng = R.RRIEngine(X, 64, order='rri')
+    p = eng.params()
+    W, T = W0.clone(), T0.clone()
+    o0 = eng.objective(W, T)
+    assert eng.sweeps(W, T, 1, p) == 0
+    o1 = eng.objective(W, T)
+    assert o1 < o0
+    assert float(W.min()) >= 0.0 and float(T.min()) >= 0.0
+    sT, sW = eng.topic_sums()
+    assert np.allclose(sT, T.double().sum(1).cpu().numpy(), rtol=1e-5)      # nmf.py:757
+    assert np.allclose(sW, W.double().sum(0).cpu().numpy(), rtol=1e-5)      # nmf.py:793
+    Wb, Tb = W0.clone(), T0.clone()
+    eng.sweeps(Wb, Tb, 1, p)
+    assert torch.equal(W, Wb) and torch.equal(T, Tb)
+    eng.close()

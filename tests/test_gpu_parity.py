@@ -308,6 +308,33 @@ def test_cfg3_shape_fp32_tf32_relerr(R):
         assert abs(re_o - re_g) < F32_RELERR_TOL, (order, math, re_o, re_g)
 
 
+def test_cfg5_shape_k128_relerr(R):
+    """config-5 columns and rank (d=20000, k=128) on a row subsample: TF32 block order within 1e-4."""
+    n, d, k = 1536, 20000, 128
+    X, W0, T0 = orc.synth(n, d, k, k, sigma=0.05, seed=2)
+    o = orc.nmf_oracle(X, k, W0, T0, max_iter=2, order='hals')
+    out = run(R, X.astype(np.float32), k, W0.astype(np.float32), T0.astype(np.float32), max_iter=2,
+              update_order='hals', math='tf32')
+    re_o = orc.rel_error(X, o['W'], o['T'])
+    re_g = orc.rel_error(X, out['W'].astype(np.float64), out['T'].astype(np.float64))
+    assert abs(re_o - re_g) < F32_RELERR_TOL, (re_o, re_g)
+
+
+def test_cfg4_shape_masked_relerr(R):
+    """config-4 columns, rank and mask density (d=20000, k=50, 5 % observed, ub_t=1) on a row subsample:
+    the tensor-core masked path and the IEEE fp32 path both land within 1e-4 of the fp64 oracle."""
+    n, d, k = 768, 20000, 50
+    X, W0, T0, M = orc.synth(n, d, k, k, sigma=0.05, seed=4, mask_density=0.05)
+    X = X / X.max()
+    o = orc.nmf_oracle(X, k, W0, T0, max_iter=1, W_mat=M, t_row_sum=1.0)
+    re_o = orc.rel_error(X, o['W'], o['T'], M)
+    for math in ('tf32', 'ieee'):
+        out = run(R, X.astype(np.float32), k, W0.astype(np.float32), T0.astype(np.float32), max_iter=1,
+                  W_mat=torch.from_numpy(M.astype(np.uint8)), t_row_sum=1.0, math=math)
+        re_g = orc.rel_error(X, out['W'].astype(np.float64), out['T'].astype(np.float64), M)
+        assert abs(re_o - re_g) < F32_RELERR_TOL, (math, re_o, re_g)
+
+
 def test_gemm_nt_tf32_vs_torch(R, cuda_device):
     torch.manual_seed(0)
     for M, N, K in ((128, 64, 64), (1000, 64, 2000), (4096, 128, 777 * 4), (300, 10, 500), (257, 50, 1028)):
