@@ -45,6 +45,16 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------
+def load_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
+    configuration (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None"""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    try:
+        return json.load(open(p)).get(key)
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(p):
@@ -274,7 +284,9 @@ def main_ours(args):
     alg_bytes = float(e - b) * d * es                       # one read of the local X per launch
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src, 'kernel_ms': kms,
+                'frac': achieved / peak,
+                'traffic': load_traffic('%s/%s/%s/rows%d' % (args.config, args.order, math, e - b)),
+                'peak_source': peak_src, 'kernel_ms': kms,
                 'algorithmic_bytes_per_launch': alg_bytes, 'launches_per_sweep': passes,
                 'sweep_effective_gbs': passes * alg_bytes / (ms_per_step * 1e-3) / 1e9,
                 'kernel_share_of_step': passes * kms / ms_per_step}

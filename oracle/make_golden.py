@@ -172,6 +172,16 @@ def main():
     d['W_est'], d['T_est'] = r['W'], r['T']
     np.savez_compressed(os.path.join(OUT, 'text_tm_f64.npz'), **d)
 
+    # ---------------------------------------------------------------- topic reset (default reset_topic_method)
+    # a case where a topic collapses to zero in the first sweep: the reference re-seeds it from the document
+    # with the largest positive residual (nmf.py:762-783)
+    rs = np.random.RandomState(33 + 57)
+    X, W0, T0 = rs.rand(33, 57), rs.rand(33, 8), rs.rand(8, 57)
+    r = ref.nmf.nmf(X, 8, W_in=W0, T_in=T0, max_iter=6, compute_obj_each_iter=True, eps_stop=-1.0)
+    np.savez_compressed(os.path.join(OUT, 'reset_rri_f64.npz'), W=r['W'], T=r['T'],
+                        obj_history=np.array(r['obj_history']),
+                        resets_remaining=np.array([ref.nmf.n_resets_remaining]))
+
     # ---------------------------------------------------------------- reference test replay (App. B.3)
     # NNDSVD-initialised (depends on sklearn's randomized_svd) -> scalar regression goldens only
     rep = {}

@@ -236,6 +236,8 @@ def sweep(X, W, T, M=None, order='rri', fix_W=False, fix_T=False,
         sW[t] = np.sum(W[:, t])                                # :793
         if check_zero and sW[t] <= ZERO_TOPIC_TOL:
             raise ZeroTopic('W', t)
+        assert np.all(W[:, t] >= 0), 'W contains negative entries'     # :475
+        assert np.sum(W[:, t]) > 0, 'W[:, t] sums to 0'                 # :476
 
     if order == 'rri':
         for t in range(k):                                     # :415

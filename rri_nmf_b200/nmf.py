@@ -301,8 +301,6 @@ def _sweep_with_resets(engine, Xd, W, T, params, a, state):
     method = a['reset_topic_method']
 
     def reset(t):
-        if state['n_resets_remaining'] == 0:
-            return
         state['n_resets_remaining'] -= 1
         if method == 'max_resid_document':
             R = (Xd - W @ T).clamp_(min=0)
@@ -314,47 +312,38 @@ def _sweep_with_resets(engine, Xd, W, T, params, a, state):
             if a['fix_reset_seed']:
                 np.random.seed(t + int(torch.argmax(T[t, :])))
             r = np.random.rand(1, engine.d)
-            T[t, :] = torch.from_numpy(r / r.sum()).to(T)
+            T[t, :] = torch.from_numpy(r / r.sum()).to(T).reshape(-1)
             W[:, t] = torch.from_numpy(np.random.rand(engine.n)).to(W)
         else:
             raise ValueError('unknown reset_topic_method %r' % (method,))
 
-    t = 0
-    while t < k:
+    for t in range(k):
         W_save, T_save = W.clone(), T.clone()
         f = engine.topics(W, T, t, t + 1, params)
         sT, sW = engine.topic_sums()
-        if f & _lib.FLAG_ZERO_T and sT[t] <= 1e-10 and state['n_resets_remaining'] > 0:
-            # the reference resets right after the T-step, then runs the W-step on the re-seeded topic
+        if sT[t] <= 1e-10 and state['n_resets_remaining'] > 0:
+            # the T row came out empty: keep only the T-step of this attempt, re-seed the topic, then run the
+            # W-step on the re-seeded row (the first attempt's W-step saw a zero denominator: drop its flags)
             W.copy_(W_save)
+            T_new_row = T[t, :].clone()
             T.copy_(T_save)
-            _t_step_only(engine, W, T, t, params)
+            T[t, :] = T_new_row
             reset(t)
             _w_step_only(engine, W, T, t, params)
-            sT, sW = engine.topic_sums()
-            f &= ~_lib.FLAG_ZERO_T
-        if sW[t] <= 1e-10 and state['n_resets_remaining'] > 0:
-            reset(t)
+            f = 0
+            sW_t = float(W[:, t].sum())
+        else:
+            sW_t = sW[t]
+        if sW_t <= 1e-10 and state['n_resets_remaining'] > 0:
+            reset(t)                                      # nmf.py:796-816
             f &= ~_lib.FLAG_ZERO_W
         flags_all |= f
-        t += 1
     return flags_all
 
 
-def _t_step_only(engine, W, T, t, params):
-    """T-step of topic t alone: run the topic on copies and keep only the new T row."""
-    W2, T2 = W.clone(), T.clone()
-    engine.topics(W2, T2, t, t + 1, params)
-    T[t, :] = T2[t, :]
-
-
 def _w_step_only(engine, W, T, t, params):
-    """W-step of topic t with T frozen: a fix_T sweep restricted to column t is a single row-local
-    solve; with T fixed, columns j != t are inputs only, so run fix_T topics on a copy and keep column t.
-    (nmf.py:462-469 with the current T.)"""
-    import copy
-    p2 = copy.copy(params)
-    # W-only step for one topic == the reference W-step: numer = X T_t' - W (T T_t')_{t->0}
+    """W-step of topic t alone (nmf.py:462-469 with the current T), used only on the rare reset path right after
+    a topic was re-seeded; plain torch ops on the device tensors."""
     Tt = T[t, :]
     h = T @ Tt
     nt = float(h[t])

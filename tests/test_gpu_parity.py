@@ -259,6 +259,18 @@ def test_zero_topic_raises_like_reference(R):
         run(R, X, 8, W0, T0, max_iter=5)
 
 
+def test_topic_reset_matches_reference(R):
+    """default reset_topic_method='max_resid_document': a topic that empties in the first sweep is re-seeded
+    from the document with the largest positive residual, exactly where the reference does it
+    (nmf.py:762-783); golden = unmodified reference on the same inputs."""
+    g = golden('reset_rri_f64.npz')
+    rs = np.random.RandomState(33 + 57)
+    X, W0, T0 = rs.rand(33, 57), rs.rand(33, 8), rs.rand(8, 57)
+    out = R.nmf(X, 8, W_in=W0, T_in=T0, max_iter=6, compute_obj_each_iter=True, eps_stop=-1.0)
+    assert np.allclose(out['obj_history'], g['obj_history'], rtol=1e-9)
+    assert relfro(out['W'], g['W']) < F64_TOL and relfro(out['T'], g['T']) < F64_TOL
+
+
 def test_argument_errors(R):
     X = np.random.RandomState(0).rand(20, 10)
     with pytest.raises(ValueError):
@@ -325,7 +337,6 @@ def test_cfg4_shape_masked_relerr(R):
     the tensor-core masked path and the IEEE fp32 path both land within 1e-4 of the fp64 oracle."""
     n, d, k = 768, 20000, 50
     X, W0, T0, M = orc.synth(n, d, k, k, sigma=0.05, seed=4, mask_density=0.05)
-    X = X / X.max()
     o = orc.nmf_oracle(X, k, W0, T0, max_iter=1, W_mat=M, t_row_sum=1.0)
     re_o = orc.rel_error(X, o['W'], o['T'], M)
     for math in ('tf32', 'ieee'):
