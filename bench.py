@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--rows', type=int, default=None, help='override n (debugging; the line then says so)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-rri', action='store_true', help='skip the side measurement of the reference-exact order')
     ap.add_argument('--cpu-rows', type=int, default=None)
     return ap.parse_args()
 
@@ -291,6 +292,34 @@ def main_ours(args):
                 'sweep_effective_gbs': passes * alg_bytes / (ms_per_step * 1e-3) / 1e9,
                 'kernel_share_of_step': passes * kms / ms_per_step}
 
+    # ---- side measurement: the reference-exact interleaved order on the same data (k passes over X per sweep)
+    rri_side = None
+    if args.order == 'hals' and not args.no_rri:
+        try:
+            eng_r = R.RRIEngine(X, k, order='rri', math='ieee', comm=comm)
+            Wr, Tr = W0.clone(), T0.clone()
+            eng_r.sweeps(Wr, Tr, 1, params, want_flags=False)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(2):
+                eng_r.sweeps(Wr, Tr, 1, params, want_flags=False)
+            r1.record()
+            barrier()
+            rms = r0.elapsed_time(r1) / 2
+            if world > 1:
+                tr = torch.tensor([rms], device=device, dtype=torch.float64)
+                dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+                rms = float(tr.item())
+            pk = eng_r.profile_kernel('rri_pass', Wr, Tr, 3)
+            rri_side = {'update_order': 'rri (reference-exact, nmf.py:415-476)', 'value': 1e3 / rms, 'unit': 'sweeps/s',
+                        'ms_per_step': rms, 'steps': 2, 'pass_kernel_ms': pk,
+                        'pass_kernel_gbs': alg_bytes / (pk * 1e-3) / 1e9, 'pass_kernel_frac': alg_bytes / (pk * 1e-3) / 1e9 / peak}
+            eng_r.close()
+            del Wr, Tr
+        except Exception as ex:
+            rri_side = {'error': repr(ex)[:200]}
+
     # ---- e2e: the public call with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -339,6 +368,7 @@ def main_ours(args):
                        'final_rel_error': relerr,
                        'exchange': ('nvlink peer memory (fused into the T update)' if peer_x else 'nccl all-reduce') if world > 1 else 'none'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'reference_order': rri_side,
         }
         print(json.dumps(line))
     if world > 1:

@@ -15,7 +15,11 @@
 //     a ring of NS stages: A stage = MT x 128 rows x 32 fp32, B stage = NPAD rows x 32 fp32.  The B tile
 //     (whole factor slab for this K chunk) is shared by the MT row tiles a CTA works on at once, so the
 //     factor is re-read from L2 only once per MT*128 rows of A; A uses an evict-first L2 policy, B evict-last;
-//   * accumulators live in TMEM: MT tiles of 128 lanes x NPAD fp32 columns;
+//   * accumulators live in TMEM: two buffers of MT tiles x 128 lanes x NPAD fp32 columns.  The MMA warp
+//     alternates buffers every FLUSH K-chunks (1024 K); the 8 epilogue warps drain the finished buffer into
+//     fp32 registers while the next one fills.  Besides hiding the epilogue this bounds the length of any
+//     tensor-core accumulation chain: the MMA accumulator truncates, which over K = 100 000+ rows shows as a
+//     systematic -4e-4 relative bias (tools/tf32_probe.py); the register adds are round-to-nearest;
 //   * stream-K work split: the (row super-tile, K chunk) units are divided evenly over the CTAs, so every
 //     SM streams the same number of bytes whatever M is (no wave quantisation at 157 or 196 tiles).
 //     A CTA whose segment covers a full K range writes C directly; first/last partial segments go to a
@@ -34,7 +38,8 @@ namespace {
 constexpr int BM = 128;            // rows per UMMA (M of the instruction, cta_group::1)
 constexpr int BK = 32;             // fp32 elements per 128-byte swizzle row
 constexpr int UK = 8;              // K of one tcgen05.mma kind::tf32
-constexpr int THREADS = 192;
+constexpr int THREADS = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int FLUSH = 32;           // K-chunks (x32 floats = 1024 K) accumulated in TMEM before a flush into registers
 constexpr int A_TILE_BYTES = BM * BK * 4;      // 16 KB
 constexpr int SMEM_LIMIT = 227 * 1024;
 
@@ -47,6 +52,8 @@ struct GemmParams {
     float* ws;                     // [grid][2][MT*BM*N] partial slots
     int stages;
     int tmem_cols;
+    int nbuf;                      // TMEM accumulator buffers (2 when 2*MT*NPAD <= 512 columns)
+    int flush;                     // K-chunks per TMEM accumulation run
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -181,22 +188,22 @@ __host__ __device__ __forceinline__ int64_t part_of(int64_t units, int parts, in
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
-template <int MT>
+template <int MT, int NPAD>
 __global__ void __launch_bounds__(THREADS, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p, int* err)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [A stages][B stages][barriers][tmem ptr]
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int a_stage = MT * A_TILE_BYTES;
-    const int b_stage = p.NPAD * BK * 4;
+    constexpr int a_stage = MT * A_TILE_BYTES;
+    constexpr int b_stage = NPAD * BK * 4;
     uint8_t* smA = smem;
     uint8_t* smB = smem + (size_t)p.stages * a_stage;
     uint64_t* full = reinterpret_cast<uint64_t*>(smB + (size_t)p.stages * b_stage);
     uint64_t* empty = full + p.stages;
-    uint64_t* tfull = empty + p.stages;
-    uint64_t* tempty = tfull + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+    uint64_t* tfull = empty + p.stages;       // [2] accumulator buffer filled
+    uint64_t* tempty = tfull + 2;             // [2] accumulator buffer drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t u_begin = part_start(p.units, gridDim.x, blockIdx.x);
@@ -206,8 +213,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tfull, 1);
-        mbar_init(tempty, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -240,75 +246,101 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(p.NPAD);
-            int stage = 0; uint32_t phase = 0, tphase = 0;
+            const uint32_t idesc = make_idesc(NPAD);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t run = 0;                                     // accumulation runs issued so far
             for (int64_t u = u_begin; u < u_end;) {
                 const int64_t kc0 = u % p.nk;
                 const int64_t len = (u_end - u) < (p.nk - kc0) ? (u_end - u) : (p.nk - kc0);
-                mbar_wait(tempty, tphase ^ 1, err, 2);           // epilogue has drained the accumulators
-                tc_fence_after();
-                for (int64_t i = 0; i < len; ++i) {
-                    mbar_wait(&full[stage], phase, err, 3);      // TMA bytes have landed
+                for (int64_t i0 = 0; i0 < len; i0 += p.flush, ++run) {
+                    const int64_t i1 = (i0 + p.flush) < len ? (i0 + p.flush) : len;
+                    const uint32_t b = p.nbuf == 2 ? (run & 1u) : 0u;
+                    const uint32_t use = p.nbuf == 2 ? (run >> 1) : run;       // how often buffer b was used before
+                    mbar_wait(&tempty[b], (use & 1u) ^ 1u, err, 2);            // epilogue has drained this buffer
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(smA + (size_t)stage * a_stage);
-                    const uint32_t b0 = smem_u32(smB + (size_t)stage * b_stage);
+                    const uint32_t tacc = tmem_base + b * (uint32_t)(MT * NPAD);
+                    for (int64_t i = i0; i < i1; ++i) {
+                        mbar_wait(&full[stage], phase, err, 3);               // TMA bytes have landed
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(smA + (size_t)stage * a_stage);
+                        const uint32_t b0 = smem_u32(smB + (size_t)stage * b_stage);
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
+                        for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-                        for (int ks = 0; ks < BK / UK; ++ks) {
-                            const uint64_t ad = make_desc(a0 + mt * A_TILE_BYTES + ks * UK * 4);
-                            const uint64_t bd = make_desc(b0 + ks * UK * 4);
-                            umma_tf32(tmem_base + (uint32_t)(mt * p.NPAD), ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < BK / UK; ++ks) {
+                                const uint64_t ad = make_desc(a0 + mt * A_TILE_BYTES + ks * UK * 4);
+                                const uint64_t bd = make_desc(b0 + ks * UK * 4);
+                                umma_tf32(tacc + (uint32_t)(mt * NPAD), ad, bd, idesc, (i > i0 || ks > 0) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&empty[stage]);               // frees the smem slot when the MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&empty[stage]);                   // frees the smem slot when the MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    umma_commit(&tfull[b]);                       // this accumulation run is complete
                 }
-                umma_commit(tfull);                               // accumulators complete
-                tphase ^= 1;
                 u += len;
             }
         }
     } else {
         // ===================================== epilogue =========================================
-        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-        uint32_t tphase = 0;
+        // 8 warps: warp pair (q, h) owns TMEM lanes [32q, 32q+32) and columns [h*NPAD/2, (h+1)*NPAD/2) of every tile
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        constexpr int HC = NPAD / 2;                              // columns per thread and tile
+        constexpr int NACC = MT * HC;
+        float acc[NACC];
+        uint32_t run = 0;
         const int64_t slot_elems = (int64_t)MT * BM * p.N;
         for (int64_t u = u_begin; u < u_end;) {
             const int64_t s = u / p.nk, kc0 = u % p.nk;
             const int64_t len = (u_end - u) < (p.nk - kc0) ? (u_end - u) : (p.nk - kc0);
             const bool complete = (len == p.nk);
+#pragma unroll
+            for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+            for (int64_t i0 = 0; i0 < len; i0 += p.flush, ++run) {
+                const uint32_t b = p.nbuf == 2 ? (run & 1u) : 0u;
+                const uint32_t use = p.nbuf == 2 ? (run >> 1) : run;
+                mbar_wait(&tfull[b], use & 1u, err, 4);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)(MT * NPAD) + (uint32_t)(h * HC);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                    for (int c0 = 0; c0 < HC; c0 += 16) {
+                        float v[16];
+                        tmem_ld16(tacc + (uint32_t)(mt * NPAD + c0), v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[mt * HC + c0 + j] += v[j];     // round-to-nearest fp32 adds
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[b]);
+            }
+            // ---- the segment is complete: write it out (full K range -> C, otherwise -> this CTA's partial slot)
             float* dst; int64_t ld; int64_t row_base; int64_t row_limit;
             if (complete) { dst = p.C; ld = p.ldc; row_base = s * MT * BM; row_limit = p.M; }
             else {
                 const int slot = (u == u_begin) ? 0 : 1;
                 dst = p.ws + ((int64_t)blockIdx.x * 2 + slot) * slot_elems; ld = p.N; row_base = 0; row_limit = MT * BM;
             }
-            mbar_wait(tfull, tphase, err, 4);
-            tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int64_t row = row_base + mt * BM + q * 32 + lane;
-                const bool rok = row < row_limit;
-                for (int c0 = 0; c0 < p.NPAD; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.NPAD + c0), v);
-                    if (rok) {
-                        float* o = dst + row * ld + c0;
-                        if ((c0 + 16 <= p.N) && ((ld & 3) == 0)) {
+                if (row < row_limit) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int c0 = 0; c0 < HC; c0 += 4) {
+                        const int col = h * HC + c0;
+                        float* o = dst + row * ld + col;
+                        if ((col + 4 <= p.N) && ((ld & 3) == 0)) {
+                            *reinterpret_cast<float4*>(o) = make_float4(acc[mt * HC + c0], acc[mt * HC + c0 + 1], acc[mt * HC + c0 + 2], acc[mt * HC + c0 + 3]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) if (c0 + j < p.N) o[j] = v[j];
+                            for (int j = 0; j < 4; ++j) if (col + j < p.N) o[j] = acc[mt * HC + c0 + j];
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
-            tphase ^= 1;
             u += len;
         }
     }
@@ -382,6 +414,7 @@ struct Tf32Gemm {
     int* err = nullptr;
     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
     int force_mt = 0;
+    int flush = FLUSH;
 };
 
 Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
@@ -399,7 +432,7 @@ Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
     }
     g->encode = (EncodeTiledFn)fn;
     // per-CTA partial slots: 2 x (MT*128 x N) floats, MT <= 2
-    g->ws_bytes = (size_t)sm_count * 2 * 2 * BM * (size_t)((nmax + 15) / 16 * 16) * sizeof(float);
+    g->ws_bytes = (size_t)sm_count * 2 * 2 * BM * (size_t)(nmax < 32 ? 32 : nmax) * sizeof(float);
     if (cudaMalloc(&g->ws, g->ws_bytes) != cudaSuccess || cudaMalloc(&g->err, sizeof(int)) != cudaSuccess) {
         err = "workspace allocation failed";
         delete g;
@@ -412,6 +445,8 @@ Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
     if (ev && ev[0] == '1') g->dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const char* mt = getenv("RRI_GEMM_MT");
     if (mt) g->force_mt = atoi(mt);
+    const char* fl = getenv("RRI_GEMM_FLUSH");       // 0 = never flush (one TMEM accumulation per segment)
+    if (fl) g->flush = atoi(fl);
     return g;
 }
 
@@ -446,21 +481,23 @@ static bool encode_2d(Tf32Gemm* g, CUtensorMap* tm, const float* base, int64_t r
     return true;
 }
 
-template <int MT>
-static int run_mt(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t st, std::string& err)
+template <int MT, int NPAD>
+static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t st, std::string& err)
 {
-    const int a_stage = MT * A_TILE_BYTES, b_stage = p.NPAD * BK * 4;
+    const int a_stage = MT * A_TILE_BYTES, b_stage = NPAD * BK * 4;
     const int bar_bytes = 1024;
     int stages = (SMEM_LIMIT - 1024 /*alignment slack*/ - bar_bytes) / (a_stage + b_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) { err = "not enough shared memory for two pipeline stages"; return -1; }
     p.stages = stages;
     const size_t smem = (size_t)stages * (a_stage + b_stage) + bar_bytes + 1024;
+    p.nbuf = (2 * MT * NPAD <= 512) ? 2 : 1;
     int cols = 32;
-    while (cols < MT * p.NPAD) cols <<= 1;
+    while (cols < p.nbuf * MT * NPAD) cols <<= 1;
     p.tmem_cols = cols;
+    p.flush = g->flush > 0 ? g->flush : (1 << 30);
     int64_t grid = p.units < g->sm_count ? p.units : g->sm_count;
-    auto kern = tf32_gemm_kernel<MT>;
+    auto kern = tf32_gemm_kernel<MT, NPAD>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         err = "cudaFuncSetAttribute(max dynamic smem) failed";
         return -1;
@@ -477,11 +514,11 @@ int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int6
 {
     if (!g) { err = "null contraction handle"; return -1; }
     if (N < 1 || N > 256) { err = "N must be in [1,256]"; return -1; }
-    const int npad = (N + 15) / 16 * 16;
-    if (npad > (g->nmax + 15) / 16 * 16) { err = "N exceeds the rank this handle was created for"; return -1; }
+    const int npad = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));     // TMEM columns per tile
+    if (N > g->nmax && N > 32) { err = "N exceeds the rank this handle was created for"; return -1; }
     int mt = (M > BM) ? 2 : 1;
-    if (mt * npad > 512) mt = 1;
-    if (g->force_mt == 1 || g->force_mt == 2) mt = (g->force_mt * npad <= 512) ? g->force_mt : 1;
+    if (npad == 256) mt = 1;                     // 128 accumulator registers per epilogue thread at most
+    if (g->force_mt == 1 || (g->force_mt == 2 && npad < 256)) mt = g->force_mt;
     CUtensorMap tmA, tmB;
     if (!encode_2d(g, &tmA, A, M, K, lda, mt * BM, err)) return -1;
     if (!encode_2d(g, &tmB, B, N, K, ldb, npad, err)) return -1;
@@ -492,7 +529,13 @@ int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int6
     p.units = p.n_super * p.nk;
     p.C = C; p.ldc = ldc; p.ws = g->ws;
     p.stages = 0; p.tmem_cols = 0;
-    return mt == 2 ? run_mt<2>(g, tmA, tmB, p, st, err) : run_mt<1>(g, tmA, tmB, p, st, err);
+    p.nbuf = 1; p.flush = 0;
+#define RRI_GEMM_CASE(MTv, NP) if (mt == MTv && npad == NP) return run_cfg<MTv, NP>(g, tmA, tmB, p, st, err)
+    RRI_GEMM_CASE(2, 32); RRI_GEMM_CASE(2, 64); RRI_GEMM_CASE(2, 128);
+    RRI_GEMM_CASE(1, 32); RRI_GEMM_CASE(1, 64); RRI_GEMM_CASE(1, 128); RRI_GEMM_CASE(1, 256);
+#undef RRI_GEMM_CASE
+    err = "no contraction kernel for this shape";
+    return -1;
 }
 
 }  // namespace rri
