@@ -186,8 +186,13 @@ def main_reference(args):
     cfg = dict(CONFIGS[args.config])
     if args.rows:
         cfg['n'] = args.rows
-    rows = args.cpu_rows or min(cfg['n'], max(256, cfg['n'] // 40))
-    cb = cpu_reference_sweeps(cfg, rows, sweeps=max(1, args.steps), warm=max(0, min(args.warmup, 1)))
+    # bounded sample: n/40 rows, fewer when K is large, so that K timed sweeps stay around a minute of CPU time
+    # (the port moves 2k x rows x d elements per sweep at roughly 40 GB/s on these hosts)
+    steps = max(1, args.steps)
+    es = 4 if cfg['dtype'] == 'f32' else 8
+    per_row = 2.0 * cfg['k'] * cfg['d'] * es / 40e9
+    rows = args.cpu_rows or int(min(cfg['n'], max(256, min(cfg['n'] // 40, 60.0 / (steps * per_row)))))
+    cb = cpu_reference_sweeps(cfg, rows, sweeps=steps, warm=max(0, min(args.warmup, 1)))
     line = {
         'impl': 'reference', 'metric': 'RRI sweeps/sec', 'value': cb['value'], 'unit': 'sweeps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,

@@ -79,6 +79,8 @@ int rri_peer_export(rri_handle_t h, char handle_out[64]);
 int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank, int32_t world);
 /* switch the exchange on once EVERY rank has imported successfully (the host checks); off = NCCL path */
 int rri_peer_enable(rri_handle_t h, int32_t on);
+/* unmap the peers' buffers; all ranks call it (and synchronise) BEFORE any rank destroys its handle */
+int rri_peer_close(rri_handle_t h);
 
 /* Bind the data (and optional elementwise weights W_mat) resident in device memory.  In hals order
  * the engine builds its own transposed copy of X (one extra pass, once).  nmf.py:98 (X, W_mat). */

@@ -37,6 +37,7 @@ SYMBOLS = {
     'rri_peer_export': (C.c_int, [_vp, C.c_char * 64]),
     'rri_peer_import': (C.c_int, [_vp, _cp, _i32, _i32]),
     'rri_peer_enable': (C.c_int, [_vp, _i32]),
+    'rri_peer_close': (C.c_int, [_vp]),
     'rri_bind': (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp]),
     'rri_sweeps': (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(RriParams), C.POINTER(_i32), _vp]),
     'rri_topics': (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.POINTER(RriParams), C.POINTER(_i32), _vp]),

@@ -340,6 +340,18 @@ extern "C" int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank
     return 0;
 }
 
+extern "C" int rri_peer_close(rri_handle_t h)
+{
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    h->p2p = false;
+    for (int r = 0; r < 16; ++r) {
+        if (h->peer_open[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+        h->peer_open[r] = false; h->peer_base[r] = nullptr;
+    }
+    return 0;
+}
+
 extern "C" int rri_peer_enable(rri_handle_t h, int32_t on)
 {
     if (!h) return fail("null handle");

@@ -132,10 +132,14 @@ class RRIEngine(object):
         if getattr(self, 'h', None):
             if getattr(self, 'peer_exchange', False):
                 # peers may still be reading this rank's exchange buffer: leave together
+                # (unmap the peers' buffers between two barriers, so that no rank frees a buffer that is still
+                # mapped or being read elsewhere)
                 try:
                     import torch.distributed as dist
                     if dist.is_initialized():
                         torch.cuda.synchronize(self.device)
+                        dist.barrier()
+                        self.lib.rri_peer_close(self.h)
                         dist.barrier()
                 except Exception:
                     pass
