@@ -458,11 +458,22 @@ gram_kernel(const T* __restrict__ F, int64_t m, int k, T* __restrict__ part)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
     for (int64_t rb = r0; rb < r1; rb += GR_ROWS) {
-        for (int e = tid; e < GR_ROWS * 64; e += 256) {
-            const int rr = e / 64, cc = e % 64;
-            const int64_t gr = rb + rr;
-            Fa[rr][cc] = (gr < r1 && a0 + cc < k) ? F[gr * k + a0 + cc] : T(0);
-            Fb[rr][cc] = (gr < r1 && b0 + cc < k) ? F[gr * k + b0 + cc] : T(0);
+        {   // all of this thread's loads first (one round trip per tile), then the shared-memory stores
+            T va[GR_ROWS * 64 / 256], vb[GR_ROWS * 64 / 256];
+#pragma unroll
+            for (int u = 0; u < GR_ROWS * 64 / 256; ++u) {
+                const int e = tid + u * 256;
+                const int rr = e / 64, cc = e % 64;
+                const int64_t gr = rb + rr;
+                va[u] = (gr < r1 && a0 + cc < k) ? F[gr * k + a0 + cc] : T(0);
+                vb[u] = (a0 == b0) ? va[u] : ((gr < r1 && b0 + cc < k) ? F[gr * k + b0 + cc] : T(0));
+            }
+#pragma unroll
+            for (int u = 0; u < GR_ROWS * 64 / 256; ++u) {
+                const int e = tid + u * 256;
+                Fa[e / 64][e % 64] = va[u];
+                Fb[e / 64][e % 64] = vb[u];
+            }
         }
         __syncthreads();
 #pragma unroll 8
