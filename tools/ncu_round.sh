@@ -3,7 +3,7 @@
 # Each ncu run is preceded, in the same call, by the identical command without ncu (must exit 0).
 R=${1:-r01}
 KREGEX='regex:(tf32_gemm|rri_|update_rows|gram_|reduce_|colsum|transpose|simt_gemm|wrri|objective|norms|project|finalize|flag_|partials)'
-HALS="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu"
+HALS="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-rri"
 RRI="python bench.py --order rri --steps 1 --warmup 1 --no-e2e --no-cpu"
 mkdir -p gpurun_out
 $HALS > gpurun_out/${R}_hals_plain.log 2>&1 &&
