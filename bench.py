@@ -298,6 +298,39 @@ def main_ours(args):
                 'sweep_effective_gbs': passes * alg_bytes / (ms_per_step * 1e-3) / 1e9,
                 'kernel_share_of_step': passes * kms / ms_per_step}
 
+    # ---- e2e: the public call with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        try:
+            Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
+            Xh.copy_(X)
+            Wh, Th = W0.cpu().pin_memory(), T0.cpu().pin_memory()
+            eng.close()
+            torch.cuda.synchronize()
+            s_e2e = args.steps
+            barrier()
+            t0 = time.perf_counter()
+            out = R.nmf(Xh.numpy(), k, W_in=Wh.numpy(), T_in=Th.numpy(), max_iter=s_e2e, reset_topic_method=None,
+                        max_time=1e9, update_order=args.order, math=math, device=device, comm=comm)
+            _ = float(out['W'][0, 0])
+            t_call = time.perf_counter() - t0
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([dt], device=device, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            hb = (Xh.numel() + Wh.numel() + Th.numel()) * es * world
+            db = (Wh.numel() + Th.numel()) * es * world
+            e2e = {'value': s_e2e / dt, 'unit': 'sweeps/s', 'h2d_bytes_per_step': hb / s_e2e,
+                   'd2h_bytes_per_step': db / s_e2e,
+                   'what': 'rri_nmf_b200.nmf(X_host, k, W_in, T_in, max_iter=%d) from pinned host arrays: H2D of X/W/T, '
+                           '%d sweeps, D2H of W/T; %.3f s total' % (s_e2e, s_e2e, dt),
+                   'rank0_phases_s': dict(out.get('timing', {}), call_s=t_call)}
+        except Exception as ex:        # host RAM too small for a pinned copy, etc.
+            e2e = {'value': None, 'unit': 'sweeps/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None,
+                   'error': repr(ex)[:200]}
+
     # ---- side measurement: the reference-exact interleaved order on the same data (k passes over X per sweep)
     rri_side = None
     if args.order == 'hals' and not args.no_rri:
@@ -325,37 +358,6 @@ def main_ours(args):
             del Wr, Tr
         except Exception as ex:
             rri_side = {'error': repr(ex)[:200]}
-
-    # ---- e2e: the public call with HOST buffers (pinned), copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        try:
-            Xh = torch.empty(X.shape, dtype=X.dtype, pin_memory=True)
-            Xh.copy_(X)
-            Wh, Th = W0.cpu().pin_memory(), T0.cpu().pin_memory()
-            eng.close()
-            torch.cuda.synchronize()
-            s_e2e = args.steps
-            barrier()
-            t0 = time.perf_counter()
-            out = R.nmf(Xh.numpy(), k, W_in=Wh.numpy(), T_in=Th.numpy(), max_iter=s_e2e, reset_topic_method=None,
-                        max_time=1e9, update_order=args.order, math=math, device=device, comm=comm)
-            _ = float(out['W'][0, 0])
-            barrier()
-            dt = time.perf_counter() - t0
-            if world > 1:
-                tt = torch.tensor([dt], device=device, dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt = float(tt.item())
-            hb = (Xh.numel() + Wh.numel() + Th.numel()) * es * world
-            db = (Wh.numel() + Th.numel()) * es * world
-            e2e = {'value': s_e2e / dt, 'unit': 'sweeps/s', 'h2d_bytes_per_step': hb / s_e2e,
-                   'd2h_bytes_per_step': db / s_e2e,
-                   'what': 'rri_nmf_b200.nmf(X_host, k, W_in, T_in, max_iter=%d) from pinned host arrays: H2D of X/W/T, '
-                           '%d sweeps, D2H of W/T; %.3f s total' % (s_e2e, s_e2e, dt)}
-        except Exception as ex:        # host RAM too small for a pinned copy, etc.
-            e2e = {'value': None, 'unit': 'sweeps/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None,
-                   'error': repr(ex)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

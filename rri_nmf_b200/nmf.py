@@ -151,6 +151,8 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         if tuple(np.shape(T_in)) != (k, d):
             raise ValueError('T_in has wrong dimensions, must be k*d')
         T0 = T_in
+    timing = {}
+    _t0 = time.perf_counter()
     with torch.cuda.device(device):
         Xd = _to_device(X, device, dtype)
         # np.maximum(W_in, 0) makes copies: the caller's arrays are never mutated (nmf.py:867-868)
@@ -167,12 +169,20 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
             else:
                 Md = _to_device(W_mat, device, dtype)
 
+        if numpy_io:
+            torch.cuda.current_stream(device).synchronize()
+        timing['to_device_s'] = time.perf_counter() - _t0          # host -> device copies of X, W, T (and W_mat)
+        _t1 = time.perf_counter()
         own_engine = engine is None
         if engine is None:
             engine = RRIEngine(Xd, k, W_mat=Md, order=update_order, math=math, comm=comm)
+        timing['engine_setup_s'] = time.perf_counter() - _t1       # workspace, transposed copy of X, peer mapping
         keep = False
         try:
+            _t2 = time.perf_counter()
             out = _solve(engine, Xd, W, T, rtv, locals())
+            timing['solve_s'] = time.perf_counter() - _t2           # sweeps + device -> host copy of W, T
+            out['timing'] = timing
             keep = 'obj_calculator' in out        # the returned objective calculator owns the engine
             return out
         finally:
