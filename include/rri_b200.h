@@ -82,6 +82,11 @@ int rri_peer_enable(rri_handle_t h, int32_t on);
 /* unmap the peers' buffers; all ranks call it (and synchronise) BEFORE any rank destroys its handle */
 int rri_peer_close(rri_handle_t h);
 
+/* Optional, before rri_bind on a hals handle: storage [d, ldXt] (ldXt >= n rounded up to 16 bytes) owned by the
+ * caller for the engine's transposed copy of X, so that it comes from the caller's allocator (torch's caching
+ * allocator: no cudaMalloc/cudaFree of a data-sized buffer per fit). */
+int rri_set_transpose_storage(rri_handle_t h, void* Xt_dev, int64_t ldXt);
+
 /* Bind the data (and optional elementwise weights W_mat) resident in device memory.  In hals order
  * the engine builds its own transposed copy of X (one extra pass, once).  nmf.py:98 (X, W_mat). */
 int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX,
@@ -118,6 +123,10 @@ int rri_partials_T(rri_handle_t h, const void* W_dev, const void* T_dev, int32_t
  * in place (matrixops.py:5-69, :72-100); used for do_final_project_W (nmf.py:519-529),
  * project_W_each_iter (:481-484) and the initial projections (:870-878). */
 int rri_project_rows_simplex(rri_handle_t h, void* A_dev, int64_t rows, int64_t cols, double s, void* stream);
+
+/* Workspace blocks of destroyed handles are parked per device (cudaMalloc/cudaFree cost tens of ms each next to a
+ * data-sized resident matrix); this really frees them. */
+int rri_cache_trim(int32_t device);
 
 /* Counters for bench.py: kernels launched by this handle since creation / bytes of workspace. */
 int rri_stats(rri_handle_t h, int64_t* kernel_launches, int64_t* workspace_bytes);

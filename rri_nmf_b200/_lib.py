@@ -38,6 +38,7 @@ SYMBOLS = {
     'rri_peer_import': (C.c_int, [_vp, _cp, _i32, _i32]),
     'rri_peer_enable': (C.c_int, [_vp, _i32]),
     'rri_peer_close': (C.c_int, [_vp]),
+    'rri_set_transpose_storage': (C.c_int, [_vp, _vp, _i64]),
     'rri_bind': (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i64, _vp]),
     'rri_sweeps': (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(RriParams), C.POINTER(_i32), _vp]),
     'rri_topics': (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.POINTER(RriParams), C.POINTER(_i32), _vp]),
@@ -45,6 +46,7 @@ SYMBOLS = {
     'rri_objective': (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_double), _vp]),
     'rri_partials_T': (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     'rri_project_rows_simplex': (C.c_int, [_vp, _vp, _i64, _i64, C.c_double, _vp]),
+    'rri_cache_trim': (C.c_int, [_i32]),
     'rri_stats': (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     'rri_profile_kernel': (C.c_int, [_vp, _i32, _vp, _vp, _i32, C.POINTER(C.c_float), _vp]),
     'rri_gemm_nt': (C.c_int, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i64, _vp]),

@@ -10,6 +10,7 @@
 #include "../../include/rri_b200.h"
 #include "gemm_tf32_sm100.h"
 #include "common.cuh"
+#include "devmem.h"
 #include "kernels.h"
 #include "wrri_tc_sm100.h"
 
@@ -130,6 +131,7 @@ struct rri_handle_s {
     void *ypart = nullptr, *ppart = nullptr, *gpart = nullptr, *hpart = nullptr, *stat = nullptr;
     // hals order
     void *Xt = nullptr; int64_t ldxt = 0, ldwt = 0;
+    void* Xt_ext = nullptr; int64_t ldxt_ext = 0;      // caller-provided storage for the transposed copy (optional)
     void *Wt = nullptr, *Tt = nullptr, *Cpart = nullptr, *cg = nullptr /* [max(n,d)*k | k*k] */, *Hm = nullptr;
     void *gram_part = nullptr, *colsum_part = nullptr;
     int splits_t = 1, splits_w = 1, ub_blocks_t = 1, ub_blocks_w = 1, gchunks_w = 1, gchunks_t = 1;
@@ -149,8 +151,8 @@ struct rri_handle_s {
 static int ws_alloc(rri_handle_t h, void** p, size_t bytes)
 {
     if (bytes == 0) bytes = 16;
-    CK(cudaMalloc(p, bytes));
-    CK(cudaMemset(*p, 0, bytes));
+    CK(cached_malloc(p, bytes));
+    CK(cudaMemsetAsync(*p, 0, bytes, 0));          // blocks come back from the cache with old contents
     h->allocs.push_back(*p);
     h->ws_bytes += (int64_t)bytes;
     return 0;
@@ -195,7 +197,7 @@ extern "C" int rri_destroy(rri_handle_t h)
     for (int r = 0; r < 16; ++r)
         if (h->peer_open[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
     if (h->xbuf) cudaFree(h->xbuf);
-    for (void* p : h->allocs) cudaFree(p);
+    for (void* p : h->allocs) cached_free(p);
     if (h->tf32) tf32_gemm_destroy(h->tf32);
     if (h->wtc) wrri_tc_destroy(h->wtc);
     delete h;
@@ -435,7 +437,16 @@ static int bind_impl(rri_handle_t h, cudaStream_t st)
         // K-contiguous operands
         const int64_t v = 16 / (int64_t)es;
         h->ldxt = (n + v - 1) / v * v;
-        if (!h->Xt) { if (ws_alloc(h, &h->Xt, es * (size_t)d * h->ldxt)) return 1; }
+        if (h->Xt_ext) {
+            if (h->ldxt_ext < h->ldxt || h->ldxt_ext % v != 0 || (reinterpret_cast<uintptr_t>(h->Xt_ext) & 15) != 0)
+                return fail("caller-provided X' storage needs a 16-byte aligned base and a row stride >= %lld, multiple of %lld",
+                            (long long)h->ldxt, (long long)v);
+            h->Xt = h->Xt_ext; h->ldxt = h->ldxt_ext;
+        } else if (!h->Xt) {
+            CK(cached_malloc(&h->Xt, es * (size_t)d * h->ldxt));    // (no memset: fully overwritten by the transpose)
+            h->allocs.push_back(h->Xt);
+            h->ws_bytes += (int64_t)(es * (size_t)d * h->ldxt);
+        }
         launch_transpose<T>((const T*)h->X, n, d, h->ldx, (T*)h->Xt, h->ldxt, st);
         h->launches++;
         CKL();
@@ -451,6 +462,14 @@ static int bind_impl(rri_handle_t h, cudaStream_t st)
             if (ws_alloc(h, &h->stat, es * (size_t)(d + ks))) return 1;
         }
     }
+    return 0;
+}
+
+extern "C" int rri_set_transpose_storage(rri_handle_t h, void* Xt_dev, int64_t ldXt)
+{
+    if (!h) return fail("null handle");
+    if (h->X) return fail("rri_set_transpose_storage must be called before rri_bind");
+    h->Xt_ext = Xt_dev; h->ldxt_ext = ldXt;
     return 0;
 }
 
@@ -960,6 +979,13 @@ extern "C" int rri_project_rows_simplex(rri_handle_t h, void* A_dev, int64_t row
     else launch_project_rows_simplex<double>((double*)A_dev, rows, cols, s, st);
     h->launches++;
     CKL();
+    return 0;
+}
+
+extern "C" int rri_cache_trim(int32_t device)
+{
+    CK(cudaSetDevice(device));
+    cache_trim();
     return 0;
 }
 

@@ -29,6 +29,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include "devmem.h"
 #include "gemm_tf32_sm100.h"
 
 namespace rri {
@@ -433,7 +434,7 @@ Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
     g->encode = (EncodeTiledFn)fn;
     // per-CTA partial slots: 2 x (MT*128 x N) floats, MT <= 2
     g->ws_bytes = (size_t)sm_count * 2 * 2 * BM * (size_t)(nmax < 32 ? 32 : nmax) * sizeof(float);
-    if (cudaMalloc(&g->ws, g->ws_bytes) != cudaSuccess || cudaMalloc(&g->err, sizeof(int)) != cudaSuccess) {
+    if (cached_malloc((void**)&g->ws, g->ws_bytes) != cudaSuccess || cached_malloc((void**)&g->err, sizeof(int)) != cudaSuccess) {
         err = "workspace allocation failed";
         delete g;
         return nullptr;
@@ -453,8 +454,8 @@ Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
 void tf32_gemm_destroy(Tf32Gemm* g)
 {
     if (!g) return;
-    if (g->ws) cudaFree(g->ws);
-    if (g->err) cudaFree(g->err);
+    if (g->ws) cached_free(g->ws);
+    if (g->err) cached_free(g->err);
     delete g;
 }
 

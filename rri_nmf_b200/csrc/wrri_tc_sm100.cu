@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include "devmem.h"
 #include "kernels.h"
 #include "wrri_tc_sm100.h"
 
@@ -429,8 +430,8 @@ WrriTc* wrri_tc_create(int sm_count, int64_t n, int64_t d, int k, std::string& e
         return nullptr;
     }
     g->encode = (EncodeTiledFn)fn;
-    if (cudaMalloc(&g->Wp, sizeof(float) * (size_t)n * g->KP) != cudaSuccess ||
-        cudaMalloc(&g->Tp, sizeof(float) * (size_t)d * g->KP) != cudaSuccess) {
+    if (cached_malloc((void**)&g->Wp, sizeof(float) * (size_t)n * g->KP) != cudaSuccess ||
+        cached_malloc((void**)&g->Tp, sizeof(float) * (size_t)d * g->KP) != cudaSuccess) {
         err = "operand copy allocation failed";
         wrri_tc_destroy(g);
         return nullptr;
@@ -464,8 +465,8 @@ WrriTc* wrri_tc_create(int sm_count, int64_t n, int64_t d, int k, std::string& e
 void wrri_tc_destroy(WrriTc* g)
 {
     if (!g) return;
-    if (g->Wp) cudaFree(g->Wp);
-    if (g->Tp) cudaFree(g->Tp);
+    if (g->Wp) cached_free(g->Wp);
+    if (g->Tp) cached_free(g->Tp);
     delete g;
 }
 

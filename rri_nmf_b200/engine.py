@@ -99,6 +99,14 @@ class RRIEngine(object):
         if comm is not None and comm.world > 1:
             path = comm.nccl_path.encode() if comm.nccl_path else None
             check(self.lib.rri_set_comm(self.h, comm.comm, comm.rank, comm.world, path))
+        self.Xt = None
+        if order == 'hals' and self.W_mat is None:
+            # the transposed copy of X lives in a torch tensor: allocation and release go through the caching
+            # allocator instead of a cudaMalloc/cudaFree of a data-sized buffer per engine
+            v = 16 // X.element_size()
+            ldxt = (self.n + v - 1) // v * v
+            self.Xt = torch.empty((self.d, ldxt), dtype=self.dtype, device=self.device)
+            check(self.lib.rri_set_transpose_storage(self.h, _ptr(self.Xt), ldxt))
         check(self.lib.rri_bind(self.h, _ptr(self.X), int(self.X.stride(0)), _ptr(self.W_mat), mk, ldm,
                                 self._stream()))
         self.peer_exchange = False
@@ -146,6 +154,7 @@ class RRIEngine(object):
                 self.peer_exchange = False
             self.lib.rri_destroy(self.h)
             self.h = C.c_void_p()
+            self.Xt = None
 
     def __del__(self):
         try:

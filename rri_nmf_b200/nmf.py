@@ -169,9 +169,9 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
             else:
                 Md = _to_device(W_mat, device, dtype)
 
-        if numpy_io:
-            torch.cuda.current_stream(device).synchronize()
-        timing['to_device_s'] = time.perf_counter() - _t0          # host -> device copies of X, W, T (and W_mat)
+        # (no synchronisation here: the pinned host -> device copy of X keeps running while the engine allocates
+        # its workspace; the first kernel is stream-ordered behind it)
+        timing['to_device_enqueue_s'] = time.perf_counter() - _t0   # host -> device copies of X, W, T (and W_mat) issued
         _t1 = time.perf_counter()
         own_engine = engine is None
         if engine is None:
@@ -181,13 +181,15 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         try:
             _t2 = time.perf_counter()
             out = _solve(engine, Xd, W, T, rtv, locals())
-            timing['solve_s'] = time.perf_counter() - _t2           # sweeps + device -> host copy of W, T
+            timing['solve_s'] = time.perf_counter() - _t2           # (rest of the H2D copy,) sweeps, device -> host copy of W, T
             out['timing'] = timing
             keep = 'obj_calculator' in out        # the returned objective calculator owns the engine
             return out
         finally:
             if own_engine and not keep:
+                _t3 = time.perf_counter()
                 engine.close()
+                timing['teardown_s'] = time.perf_counter() - _t3
 
 
 def _solve(engine, Xd, W, T, rtv, a):
