@@ -229,6 +229,9 @@ def main_ours(args):
         dist.init_process_group('nccl', device_id=device)
         comm = NcclComm(local)
 
+    sampler = ClockSampler(local)          # started before data generation: nvidia-smi needs a second to come up
+    if rank == 0:
+        sampler.start()
     cfg = dict(CONFIGS[args.config])
     if args.rows:
         cfg['n'] = args.rows
@@ -247,9 +250,6 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     # K steps = K sweeps issued by ONE call of the engine (like nmf(max_iter=K) does): the per-call set-up
     # (transposed factor copies, flag reset) is paid once, not once per sweep
     if args.warmup > 0:
