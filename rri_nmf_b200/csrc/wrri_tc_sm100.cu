@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "devmem.h"
 #include "kernels.h"
@@ -47,6 +48,7 @@ struct TcParams {
     int groups;                            // T mode: row groups per column tile; W mode: column groups per row tile
     float* numer_part; float* denom_part;  // [groups][d] (T mode) or [groups][n] (W mode)
     int stages;
+    int xm_stages;                         // TMA ring depth of the X / mask tiles (TMA variant)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -383,6 +385,268 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant (default): X and the mask are streamed by a dedicated producer thread into a ring of
+// shared-memory stages (cp.async.bulk.tensor, zero-filled tails), several tiles ahead of the epilogue, so no
+// warp ever waits on a dependent global load: warp 0 = operand TMA + MMA issue, warp 1 = X/mask producer,
+// warps 2-9 = epilogue.  One CTA per SM (the ring wants the shared memory).
+// ------------------------------------------------------------------------------------------------
+constexpr int EPI_WARPS_TMA = 16;                    // 4 warps per TMEM lane quarter (16 columns each)
+constexpr int THREADS_TMA = 32 * (2 + EPI_WARPS_TMA);
+constexpr int ROWS_TMA = TM / (2 * EPI_WARPS_TMA);  // row steps per thread in the element-wise pass
+constexpr int X_TILE_BYTES = TM * TN * 4;            // 32 KB
+
+__device__ __forceinline__ void epi_barrier_tma()
+{
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS_TMA * 32) : "memory");
+}
+
+template <int MODE, int MK>
+__global__ void __launch_bounds__(THREADS_TMA, 1)
+wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmT,
+                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmM, TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int M_TILE_BYTES = MK == MK_U8 ? TM * TN : TM * TN * 4;
+    constexpr int XM_STAGE = X_TILE_BYTES + M_TILE_BYTES;
+    const int nchunk = p.KP / BK;
+    const int w_bytes = nchunk * W_CHUNK_BYTES, t_bytes = nchunk * T_CHUNK_BYTES;
+    const int fixed_bytes = MODE == 0 ? t_bytes : w_bytes;
+    const int var_bytes = MODE == 0 ? w_bytes : t_bytes;
+    const int var_chunk = MODE == 0 ? W_CHUNK_BYTES : T_CHUNK_BYTES;
+    const int fixed_chunk = MODE == 0 ? T_CHUNK_BYTES : W_CHUNK_BYTES;
+    uint8_t* sm_fixed = smem;
+    uint8_t* sm_var = smem + fixed_bytes;
+    uint8_t* sm_xm = sm_var + (size_t)p.stages * var_bytes;                       // [xm_stages][X tile | mask tile]
+    float* Ds = reinterpret_cast<float*>(sm_xm + (size_t)p.xm_stages * XM_STAGE);     // [TM][DS_LD]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Ds + TM * DS_LD);
+    uint64_t* fixed_full = bars;            // 1
+    uint64_t* var_full = bars + 1;          // [2]
+    uint64_t* var_free = bars + 3;          // [2]
+    uint64_t* acc_full = bars + 5;          // [2]
+    uint64_t* acc_free = bars + 7;          // [2]
+    uint64_t* xm_full = bars + 9;           // [4]
+    uint64_t* xm_free = bars + 13;          // [4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fixed_tile = blockIdx.x;
+    const int nvar_total = MODE == 0 ? p.tiles_r : p.tiles_c;
+    int vb, ve;
+    {
+        const int q = nvar_total / (int)gridDim.y, r = nvar_total % (int)gridDim.y, g = blockIdx.y;
+        vb = q * g + (g < r ? g : r);
+        ve = vb + q + (g < r ? 1 : 0);
+    }
+    const int ntiles = ve - vb;
+    const int var_rows = MODE == 0 ? TM : TN, fixed_rows = MODE == 0 ? TN : TM;
+
+    if (threadIdx.x == 0) {
+        mbar_init(fixed_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&var_full[s], 1); mbar_init(&var_free[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 4); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&xm_full[s], 1); mbar_init(&xm_free[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ operand TMA + MMA control thread ========================
+        if (lane == 0 && ntiles > 0) {
+            const CUtensorMap* tm_fixed = MODE == 0 ? &tmT : &tmW;
+            const CUtensorMap* tm_var = MODE == 0 ? &tmW : &tmT;
+            mbar_expect_tx(fixed_full, (uint32_t)fixed_bytes);
+            for (int c = 0; c < nchunk; ++c) tma_load_2d(tm_fixed, sm_fixed + c * fixed_chunk, fixed_full, c * BK, fixed_tile * fixed_rows);
+            const int S = p.stages;
+            for (int s0 = 0; s0 < S && s0 < ntiles; ++s0) {
+                mbar_expect_tx(&var_full[s0], (uint32_t)var_bytes);
+                for (int c = 0; c < nchunk; ++c)
+                    tma_load_2d(tm_var, sm_var + (size_t)s0 * var_bytes + c * var_chunk, &var_full[s0], c * BK, (vb + s0) * var_rows);
+            }
+            mbar_wait(fixed_full, 0);
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            for (int n = 0; n < ntiles; ++n) {
+                const int s = n % S, a = n & 1;
+                mbar_wait(&var_full[s], (n / S) & 1);
+                mbar_wait(&acc_free[a], ((n >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t var0 = smem_u32(sm_var + (size_t)s * var_bytes), fix0 = smem_u32(sm_fixed);
+                const uint32_t w0 = MODE == 0 ? var0 : fix0;
+                const uint32_t t0 = MODE == 0 ? fix0 : var0;
+                for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+                    for (int ks = 0; ks < BK / UK; ++ks) {
+                        umma_tf32(tmem_base + (uint32_t)(a * TN), make_desc(w0 + c * W_CHUNK_BYTES + ks * UK * 4),
+                                  make_desc(t0 + c * T_CHUNK_BYTES + ks * UK * 4), idesc, (c > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&var_free[s]);
+                umma_commit(&acc_full[a]);
+                if (n + S < ntiles) {
+                    mbar_wait(&var_free[s], (n / S) & 1);
+                    mbar_expect_tx(&var_full[s], (uint32_t)var_bytes);
+                    for (int c = 0; c < nchunk; ++c)
+                        tma_load_2d(tm_var, sm_var + (size_t)s * var_bytes + c * var_chunk, &var_full[s], c * BK, (vb + n + S) * var_rows);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ X / mask producer =======================================
+        if (lane == 0) {
+            const int NS = p.xm_stages;
+            for (int n = 0; n < ntiles; ++n) {
+                const int s = n % NS;
+                const int rt = MODE == 0 ? (vb + n) : fixed_tile, ctile = MODE == 0 ? fixed_tile : (vb + n);
+                mbar_wait(&xm_free[s], ((n / NS) & 1) ^ 1);            // the epilogue has released this stage
+                mbar_expect_tx(&xm_full[s], (uint32_t)XM_STAGE);
+                uint8_t* dst = sm_xm + (size_t)s * XM_STAGE;
+                tma_load_2d(&tmX, dst, &xm_full[s], ctile * TN, rt * TM);
+                tma_load_2d(&tmM, dst + X_TILE_BYTES, &xm_full[s], ctile * TN, rt * TM);
+            }
+        }
+    } else {
+        // ======================================= epilogue ========================================
+        const int ew = warp - 2;                 // 0..15
+        const int q = warp & 3;                  // TMEM lane quarter this warp may read
+        constexpr int R = ROWS_TMA;
+        constexpr int RSTEP = 2 * EPI_WARPS_TMA;     // rows covered by all warps in one step
+        const int cl = 4 * (lane & 15);
+        const int rsub = 2 * ew + (lane >> 4);
+        float nacc[MODE == 0 ? 4 : R], dacc[MODE == 0 ? 4 : R];
+#pragma unroll
+        for (int i = 0; i < (MODE == 0 ? 4 : R); ++i) { nacc[i] = 0.f; dacc[i] = 0.f; }
+        const int NS = p.xm_stages;
+
+        // row t of T' and column t of W for this thread's columns / rows of a tile: the only global loads left in
+        // the epilogue (L2-resident factors).  They are requested one tile ahead so their latency never shows.
+        auto load_factors = [&](int n, float tt_out[4], float wts_out[R]) {
+            const int rt = MODE == 0 ? (vb + n) : fixed_tile, ctile = MODE == 0 ? fixed_tile : (vb + n);
+            const int64_t i0 = (int64_t)rt * TM, gc = (int64_t)ctile * TN + cl;
+            const bool ok = n < ntiles;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) tt_out[v] = (ok && gc < p.d) ? __ldg(p.Tp + (gc + v) * p.KP + p.t) : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                const int64_t gi = i0 + rsub + RSTEP * rr;
+                wts_out[rr] = (ok && gi < p.n) ? __ldg(p.Wp + gi * p.KP + p.t) : 0.f;
+            }
+        };
+        float tt[4], wts[R];
+        load_factors(0, tt, wts);
+
+        for (int n = 0; n < ntiles; ++n) {
+            const int a = n & 1, s = n % NS;
+            float ttn[4], wtsn[R];
+            load_factors(n + 1, ttn, wtsn);
+            mbar_wait(&acc_full[a], (n >> 1) & 1);
+            tc_fence_after();
+            {   // TMEM -> shared: the four warps of a lane quarter take 16 columns each
+                const int col = (ew >> 2) * 16;
+                const int row = q * 32 + lane;
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + col), v);
+                float4* o = reinterpret_cast<float4*>(Ds + row * DS_LD + col);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                o[3] = make_float4(v[12], v[13], v[14], v[15]);
+            }
+            mbar_wait(&xm_full[s], (n / NS) & 1);                     // this tile's X and mask have landed
+            tc_fence_before();
+            epi_barrier_tma();                                        // product tile staged; TMEM reads done
+            if (lane == 0 && ew < 4) mbar_arrive(&acc_free[a]);
+
+            const float* Xs = reinterpret_cast<const float*>(sm_xm + (size_t)s * XM_STAGE);
+            const uint8_t* Ms = sm_xm + (size_t)s * XM_STAGE + X_TILE_BYTES;
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                const int r = rsub + RSTEP * rr;
+                float m[4];
+                bool any;
+                if (MK == MK_U8) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(Ms + r * TN + cl);
+                    any = w != 0u;
+                    m[0] = (float)(w & 0xffu); m[1] = (float)((w >> 8) & 0xffu); m[2] = (float)((w >> 16) & 0xffu); m[3] = (float)(w >> 24);
+                } else {
+                    const float4 mv = *reinterpret_cast<const float4*>(Ms + (size_t)(r * TN + cl) * 4);
+                    m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
+                    any = (mv.x != 0.f) | (mv.y != 0.f) | (mv.z != 0.f) | (mv.w != 0.f);
+                }
+                if (any) {
+                    const float4 xv = *reinterpret_cast<const float4*>(Xs + r * TN + cl);
+                    const float4 dv = *reinterpret_cast<const float4*>(Ds + r * DS_LD + cl);
+                    const float wt = wts[rr];
+                    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+                    const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const float res = m[v] * (x[v] - dd[v] + wt * tt[v]);          // M o (X - W_{t->0} T)
+                        if (MODE == 0) {
+                            nacc[v] = fmaf(wt, res, nacc[v]);
+                            dacc[v] = fmaf(wt * wt, m[v], dacc[v]);
+                        } else {
+                            nacc[rr] = fmaf(res, tt[v], nacc[rr]);
+                            dacc[rr] = fmaf(m[v] * tt[v], tt[v], dacc[rr]);
+                        }
+                    }
+                }
+            }
+            epi_barrier_tma();                                        // Ds and this X/mask stage are free again
+            if (ew == 0 && lane == 0) mbar_arrive(&xm_free[s]);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) tt[v] = ttn[v];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) wts[rr] = wtsn[rr];
+        }
+
+        if (MODE == 0) {
+            float* red = Ds;                                          // [2*EPI_WARPS_TMA][2][TN]
+            const int slot = 2 * ew + (lane >> 4);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                red[(slot * 2 + 0) * TN + cl + v] = nacc[v];
+                red[(slot * 2 + 1) * TN + cl + v] = dacc[v];
+            }
+            epi_barrier_tma();
+            const int e = threadIdx.x - 64;                           // 0..511
+            if (e < 2 * TN) {
+                const int which = e / TN, cc = e % TN;
+                float sacc = 0.f;
+#pragma unroll
+                for (int w = 0; w < 2 * EPI_WARPS_TMA; ++w) sacc += red[(w * 2 + which) * TN + cc];
+                const int64_t gcol = (int64_t)fixed_tile * TN + cc;
+                if (gcol < p.d) (which ? p.denom_part : p.numer_part)[(int64_t)blockIdx.y * p.d + gcol] = sacc;
+            }
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                float a = nacc[rr], b = dacc[rr];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                const int64_t gi = (int64_t)fixed_tile * TM + rsub + RSTEP * rr;
+                if ((lane & 15) == 0 && gi < p.n) {
+                    p.numer_part[(int64_t)blockIdx.y * p.n + gi] = a;
+                    p.denom_part[(int64_t)blockIdx.y * p.n + gi] = b;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -412,6 +676,13 @@ struct WrriTc {
     CUtensorMap tmW, tmT;
     int stages[2] = {1, 2};
     size_t smem[2] = {0, 0};
+    // TMA variant
+    const void* mapX = nullptr; const void* mapM = nullptr; int64_t map_ldx = 0, map_ldm = 0; int map_mk = -1;
+    CUtensorMap tmX, tmM;
+    bool tma_ok = false;
+    int tma_stages[2][3] = {{1, 1, 1}, {1, 1, 1}};      // [mode][mask kind] operand stages
+    int tma_xm[2][3] = {{0, 0, 0}, {0, 0, 0}};          // [mode][mask kind] X/mask ring depth (0 = does not fit)
+    size_t tma_smem[2][3] = {{0, 0, 0}, {0, 0, 0}};
 };
 
 WrriTc* wrri_tc_create(int sm_count, int64_t n, int64_t d, int k, std::string& err)
@@ -494,6 +765,51 @@ void wrri_tc_load_factors(WrriTc* g, const float* W, const float* T, cudaStream_
     pad_copy_kernel<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(T, g->d, g->k, g->d, 1, g->Tp, g->KP);
 }
 
+static bool tma_prepare(WrriTc* g, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm)
+{
+    if (g->mapX == X && g->mapM == M && g->map_ldx == ldx && g->map_ldm == ldm && g->map_mk == mk) return g->tma_ok;
+    g->mapX = X; g->mapM = M; g->map_ldx = ldx; g->map_ldm = ldm; g->map_mk = mk; g->tma_ok = false;
+    const size_t mes = mk == MK_U8 ? 1 : 4;
+    if ((reinterpret_cast<uintptr_t>(X) & 15) || (ldx * 4) % 16 || (reinterpret_cast<uintptr_t>(M) & 15) || (ldm * mes) % 16) return false;
+    auto enc = [&](CUtensorMap* tm, const void* base, CUtensorMapDataType dt, size_t es, int64_t ld) -> bool {
+        cuuint64_t gdim[2] = {(cuuint64_t)g->d, (cuuint64_t)g->n};
+        cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
+        cuuint32_t box[2] = {(cuuint32_t)TN, (cuuint32_t)TM};
+        cuuint32_t estr[2] = {1, 1};
+        return g->encode(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (!enc(&g->tmX, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ldx)) return false;
+    if (!enc(&g->tmM, M, mk == MK_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, mes, ldm)) return false;
+    // shared-memory plan per mode: operands + product tile + as many X/mask stages as fit (at least 2)
+    const int w_bytes = (g->KP / BK) * W_CHUNK_BYTES, t_bytes = (g->KP / BK) * T_CHUNK_BYTES;
+    const size_t ds = sizeof(float) * TM * DS_LD + 512 + 1024;
+    const size_t xm = (size_t)X_TILE_BYTES + (mk == MK_U8 ? (size_t)TM * TN : (size_t)TM * TN * 4);
+    for (int mode = 0; mode < 2; ++mode) {
+        const size_t fixed = mode == 0 ? t_bytes : w_bytes, var = mode == 0 ? w_bytes : t_bytes;
+        // two operand stages first (with one, every tile waits a full L2 round trip for its W / T' tile after the
+        // previous MMA retires: measured 1.75 us per tile), then as many X/mask stages as still fit (>= 2)
+        const size_t room = (size_t)227 * 1024;
+        int S = 0, ns = 0;
+        static const char* force_s = getenv("RRI_WRRI_OPERAND_STAGES");
+        for (int s_try = 2; s_try >= 1; --s_try) {
+            if (force_s && atoi(force_s) != s_try) continue;
+            const size_t base = fixed + (size_t)s_try * var + ds;
+            if (base >= room) continue;
+            int n_try = (int)((room - base) / xm);
+            if (n_try > 4) n_try = 4;
+            if (n_try >= 2) { ns = n_try; S = s_try; break; }
+        }
+        if (S < 1 || ns < 2) { g->tma_xm[mode][mk] = 0; continue; }
+        g->tma_stages[mode][mk] = S;
+        g->tma_xm[mode][mk] = ns;
+        g->tma_smem[mode][mk] = fixed + (size_t)S * var + ds + (size_t)ns * xm;
+    }
+    g->tma_ok = true;
+    return true;
+}
+
 template <int MODE>
 static int launch_mode(WrriTc* g, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm, int t, float* numer_part,
                        float* denom_part, int groups, cudaStream_t st, std::string& err)
@@ -501,21 +817,32 @@ static int launch_mode(WrriTc* g, const float* X, int64_t ldx, const void* M, in
     TcParams p;
     p.X = X; p.ldx = ldx; p.M = M; p.ldm = ldm; p.Wp = g->Wp; p.Tp = g->Tp; p.n = g->n; p.d = g->d; p.KP = g->KP; p.t = t;
     p.tiles_r = (int)((g->n + TM - 1) / TM); p.tiles_c = (int)((g->d + TN - 1) / TN);
-    p.groups = groups; p.numer_part = numer_part; p.denom_part = denom_part; p.stages = g->stages[MODE];
+    p.groups = groups; p.numer_part = numer_part; p.denom_part = denom_part; p.stages = g->stages[MODE]; p.xm_stages = 0;
     dim3 grid(MODE == 0 ? p.tiles_c : p.tiles_r, groups);
-    if (mk == MK_U8) {
-        if (ldm % 4 != 0) { err = "u8 masks need a row stride that is a multiple of 4"; return -1; }
+    if (mk != MK_U8 && mk != MK_REAL) { err = "the tensor-core WRRI path needs a mask"; return -1; }
+    if (ldm % 4 != 0) { err = "mask rows need a stride that is a multiple of 4 elements"; return -1; }
+    static const bool no_tma = getenv("RRI_WRRI_NO_TMA") != nullptr;
+    if (!no_tma && tma_prepare(g, X, ldx, M, mk, ldm) && g->tma_xm[MODE][mk] >= 2) {
+        p.stages = g->tma_stages[MODE][mk];
+        p.xm_stages = g->tma_xm[MODE][mk];
+        const size_t smem = g->tma_smem[MODE][mk];
+        if (mk == MK_U8) {
+            auto kern = wrri_tc_tma_kernel<MODE, MK_U8>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, THREADS_TMA, smem, st>>>(g->tmW, g->tmT, g->tmX, g->tmM, p);
+        } else {
+            auto kern = wrri_tc_tma_kernel<MODE, MK_REAL>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, THREADS_TMA, smem, st>>>(g->tmW, g->tmT, g->tmX, g->tmM, p);
+        }
+    } else if (mk == MK_U8) {
         auto kern = wrri_tc_kernel<MODE, MK_U8>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem[MODE]);
         kern<<<grid, THREADS, g->smem[MODE], st>>>(g->tmW, g->tmT, p);
-    } else if (mk == MK_REAL) {
-        if (ldm % 4 != 0) { err = "weights need a row stride that is a multiple of 4"; return -1; }
+    } else {
         auto kern = wrri_tc_kernel<MODE, MK_REAL>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem[MODE]);
         kern<<<grid, THREADS, g->smem[MODE], st>>>(g->tmW, g->tmT, p);
-    } else {
-        err = "the tensor-core WRRI path needs a mask";
-        return -1;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return -1; }

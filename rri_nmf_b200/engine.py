@@ -81,7 +81,11 @@ class RRIEngine(object):
             if tuple(W_mat.shape) != (self.n, self.d):
                 raise ValueError('W_mat must have the shape of X')
             if W_mat.dtype == torch.uint8 or W_mat.dtype == torch.bool:
-                W_mat = W_mat.to(torch.uint8).contiguous()
+                # byte masks are kept with a row stride that is a multiple of 16 bytes (a legal TMA row)
+                ldp = (self.d + 15) // 16 * 16
+                Mp = torch.zeros((self.n, ldp), dtype=torch.uint8, device=W_mat.device)
+                Mp[:, :self.d] = W_mat.to(torch.uint8)
+                W_mat = Mp[:, :self.d]
                 mk = _lib.RRI_MASK_U8
             else:
                 W_mat = W_mat.to(self.dtype).contiguous()
