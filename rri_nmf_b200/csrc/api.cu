@@ -186,6 +186,7 @@ extern "C" int rri_create(rri_handle_t* out, int64_t n_local, int64_t d, int32_t
         rri_destroy(h);
         return 1;
     }
+    cudaStreamSynchronize(0);
     *out = h;
     return 0;
 }
@@ -338,6 +339,7 @@ extern "C" int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank
     CK(cudaMemcpy(h->d_peerP, pp.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_peerR, pr.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->d_peerFlag, pf.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(0));
     h->rank = rank; h->world = world; h->epoch = 0; h->p2p = false;     // enabled by rri_peer_enable on ALL ranks
     return 0;
 }
@@ -490,7 +492,12 @@ extern "C" int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX, const vo
     h->mk = mask_kind; h->ldm = ldM;
     h->fixT_cached = false;
     cudaStream_t st = (cudaStream_t)stream;
-    return h->dtype == RRI_F32 ? bind_impl<float>(h, st) : bind_impl<double>(h, st);
+    int rc = h->dtype == RRI_F32 ? bind_impl<float>(h, st) : bind_impl<double>(h, st);
+    if (rc) return rc;
+    // workspace zero-fills were issued on the legacy default stream: finish them before the caller's (possibly
+    // non-blocking) stream starts using the buffers
+    CK(cudaStreamSynchronize(0));
+    return 0;
 }
 
 static SolveArgs solve_args(const rri_params_t* p, bool forT)
