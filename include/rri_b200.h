@@ -92,6 +92,17 @@ int rri_set_transpose_storage(rri_handle_t h, void* Xt_dev, int64_t ldXt);
 int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX,
              const void* mask_dev, int32_t mask_kind, int64_t ldM, void* stream);
 
+/* Observed-entries binding for the recommender setting: the (i, j, rating) triples of
+ * sklearn_interface.py:78-83 as a CSR matrix of the LOCAL rows, instead of the densified X and the dense 0/1
+ * W_mat of :97-102.  rowptr_dev[n_local+1] (int64), col_dev[nnz] (int32, strictly ascending inside a row),
+ * val_dev[nnz] (element type of the handle); weight_dev[nnz] optional entry weights (NULL = 1, i.e. W_mat is the
+ * indicator of the stored entries).  A stored entry is an observed one, whatever its value.  The engine builds its
+ * column-major copy once (synchronises `stream`); the three CSR arrays must stay alive while the handle is used.
+ * Every masked entry point (rri_sweeps, rri_topics, rri_objective, rri_partials_T, rri_topic_sums) then runs
+ * nmf.py:687-701 / :735-746 with traffic proportional to nnz.  IEEE math only; a handle is bound once. */
+int rri_bind_csr(rri_handle_t h, int64_t nnz, const int64_t* rowptr_dev, const int32_t* col_dev,
+                 const void* val_dev, const void* weight_dev, void* stream);
+
 /* Run n_sweeps full sweeps in place on W_dev[n_local,k], T_dev[k,d]:  nmf.py:377, :415-476
  * (+ masked branches :687-701, :735-746; qf_min optimization.py:51-59, :75-87).
  * flags_host (may be NULL): receives the OR of RRI_FLAG_* over all sweeps (forces a stream sync).

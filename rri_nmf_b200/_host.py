@@ -17,8 +17,10 @@ def _rng(random_state):
 def initialize_nmf(X, n_components, init=None, eps=1e-6, random_state=None, row_normalize=False):
     """Initial (W, T) for X ~ W T.  init in {None, 'random', 'smart_random', 'nndsvd', 'nndsvda',
     'nndsvdar'} with the semantics of initialization.py:80-163 (NNDSVD: Boutsidis & Gallopoulos 2008
-    on a randomized partial SVD)."""
-    X = np.asarray(X)
+    on a randomized partial SVD).  X may be a scipy.sparse matrix (never densified)."""
+    import scipy.sparse as sp
+    if not sp.issparse(X):
+        X = np.asarray(X)
     n, d = X.shape
     k = int(n_components)
     if init is None:

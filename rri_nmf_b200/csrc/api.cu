@@ -141,6 +141,13 @@ struct rri_handle_s {
     TilePlan tpl{}, wpl{};
     void *numer_part = nullptr, *denom_part = nullptr, *mstat = nullptr;
     WrriTc* wtc = nullptr; int wtc_groups_t = 1, wtc_groups_w = 1;
+    // observed-entries (sparse) binding: CSR given by the caller, CSC built by rri_bind_csr
+    bool sparse = false; int64_t nnz = 0;
+    SpSide csr{}, csc{};
+    void *sp_quad = nullptr;           // [max(n,d)] packed gather records of one pass
+    void *sp_told = nullptr;           // [2][d] T[t,:] before its T-step (two topics in flight)
+    void *sp_wold = nullptr;           // [2][n] W[:,t] before its W-step
+    int* sp_err = nullptr;
     // common
     double* sums = nullptr;    // [2k] device
     int* flags = nullptr;      // device
@@ -484,6 +491,7 @@ extern "C" int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX, const vo
     if (mask_kind != RRI_MASK_NONE && !mask_dev) return fail("mask kind %d without a mask pointer", mask_kind);
     if (mask_kind != RRI_MASK_NONE && ldM < h->d) return fail("ldM < d");
     if (mask_kind < 0 || mask_kind > 2) return fail("bad mask kind %d", mask_kind);
+    if (h->sparse) return fail("this handle is bound to observed-entries (CSR) data; create a new one for dense data");
     if (h->X && ((h->mk != MK_NONE) != (mask_kind != RRI_MASK_NONE)))
         return fail("a handle cannot switch between masked and unmasked data; create a new one");
     CK(cudaSetDevice(h->device));
@@ -497,6 +505,68 @@ extern "C" int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX, const vo
     // workspace zero-fills were issued on the legacy default stream: finish them before the caller's (possibly
     // non-blocking) stream starts using the buffers
     CK(cudaStreamSynchronize(0));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// observed-entries (sparse) binding
+// -------------------------------------------------------------------------------------------------
+template <typename T>
+static int bind_csr_impl(rri_handle_t h, const int64_t* rowptr, const int32_t* col, const T* val, const T* wgt,
+                         cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d, nnz = h->nnz;
+    const int k = h->k;
+    const size_t es = sizeof(T);
+    const int64_t m = n > d ? n : d;
+    const size_t ne = (size_t)(nnz > 0 ? nnz : 1);
+    void *E_csr = nullptr, *E_csc = nullptr, *x_csc = nullptr, *w_csc = nullptr, *csc_row = nullptr, *colptr = nullptr;
+    if (ws_alloc(h, (void**)&h->obj_part, sizeof(double) * 2 * 256) || ws_alloc(h, (void**)&h->obj_out, sizeof(double) * 8)) return 1;
+    if (ws_alloc(h, &E_csr, es * ne) || ws_alloc(h, &E_csc, es * ne) || ws_alloc(h, &x_csc, es * ne)) return 1;
+    if (wgt && ws_alloc(h, &w_csc, es * ne)) return 1;
+    if (ws_alloc(h, &csc_row, sizeof(int32_t) * ne) || ws_alloc(h, &colptr, sizeof(int64_t) * (size_t)(d + 1))) return 1;
+    if (ws_alloc(h, &h->sp_quad, 4 * es * (size_t)m) || ws_alloc(h, &h->sp_told, es * 2 * (size_t)d) ||
+        ws_alloc(h, &h->sp_wold, es * 2 * (size_t)n) || ws_alloc(h, &h->mstat, es * 2 * (size_t)m) ||
+        ws_alloc(h, (void**)&h->sp_err, sizeof(int)))
+        return 1;
+    {
+        const int64_t v = 16 / (int64_t)es;
+        h->ldwt = (n + v - 1) / v * v;
+    }
+    if (ws_alloc(h, &h->Wt, es * (size_t)k * h->ldwt) || ws_alloc(h, &h->Tt, es * (size_t)d * k)) return 1;
+    CK(cudaStreamSynchronize(0));          // the zero-fills above ran on the legacy default stream
+    const int rc = sp_build_csc<T>(rowptr, col, val, wgt, n, d, nnz, (int64_t*)colptr, (int32_t*)csc_row, (T*)x_csc,
+                                   (T*)w_csc, h->sm_count, h->sp_err, st);
+    if (rc < 0)
+        return fail("malformed CSR input:%s%s%s", (-rc & 1) ? " rowptr is not a monotone [0..nnz] sequence;" : "",
+                    (-rc & 2) ? " column index outside [0,d);" : "",
+                    (-rc & 4) ? " column indices must be strictly ascending inside every row (sort and merge duplicates);" : "");
+    if (rc > 0) return fail("building the column orientation failed: %s", cudaGetErrorString((cudaError_t)rc));
+    h->csr = SpSide{n, rowptr, col, val, wgt, E_csr, nnz / n >= 512 ? 256 : 32};
+    h->csc = SpSide{d, (const int64_t*)colptr, (const int32_t*)csc_row, x_csc, w_csc, E_csc, nnz / d >= 512 ? 256 : 32};
+    h->launches += 8;
+    return 0;
+}
+
+extern "C" int rri_bind_csr(rri_handle_t h, int64_t nnz, const int64_t* rowptr_dev, const int32_t* col_dev,
+                            const void* val_dev, const void* weight_dev, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (h->X) return fail("the handle is already bound; create a new one");
+    if (nnz < 0 || nnz >= ((int64_t)1 << 31)) return fail("nnz must be in [0, 2^31) (got %lld)", (long long)nnz);
+    if (!rowptr_dev) return fail("rowptr is null");
+    if (nnz > 0 && (!col_dev || !val_dev)) return fail("col/val is null");
+    if (h->math == RRI_MATH_TF32) return fail("the observed-entries path has no contraction: create the handle with RRI_MATH_IEEE");
+    CK(cudaSetDevice(h->device));
+    h->nnz = nnz;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = h->dtype == RRI_F32
+                       ? bind_csr_impl<float>(h, rowptr_dev, col_dev, (const float*)val_dev, (const float*)weight_dev, st)
+                       : bind_csr_impl<double>(h, rowptr_dev, col_dev, (const double*)val_dev, (const double*)weight_dev, st);
+    if (rc) return rc;
+    h->sparse = true;
+    h->mk = MK_SPARSE;
+    h->X = val_dev ? val_dev : (const void*)rowptr_dev;      // "bound" marker; the dense kernels never see it
     return 0;
 }
 
@@ -775,6 +845,129 @@ static int wrri_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p
 }
 
 // -------------------------------------------------------------------------------------------------
+// observed-entries WRRI (both orders): one streaming pass over the CSC copy per T-step, over the CSR copy
+// per W-step (sparse_kernels.cu)
+// -------------------------------------------------------------------------------------------------
+struct SpPending {             // rank-one change  wo to' - wn tn'  a residual copy has not absorbed yet
+    const void *wo = nullptr, *wn = nullptr, *to = nullptr, *tn = nullptr;
+};
+struct SpState {
+    SpPending csr, csc;
+    int ct = 0, cw = 0;                 // parity of the told / wold buffers
+    const void* told_cur = nullptr;     // T[t,:] before this topic's T-step (null: no T-step preceded the W-step)
+};
+
+template <typename T>
+static void sp_refresh(rri_handle_t h, bool csr, const T* W, cudaStream_t st)
+{
+    // E = X - W T on the observed entries, from the current factors
+    if (csr) launch_sp_residual<T>(h->csr, W, (const T*)h->Tt, h->k, h->sm_count, st);
+    else launch_sp_residual<T>(h->csc, (const T*)h->Tt, W, h->k, h->sm_count, st);
+    h->launches++;
+}
+
+template <typename T>
+static int sp_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, SpState& S, cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d;
+    const T* wt = (const T*)h->Wt + (int64_t)t * h->ldwt;            // W[:,t], contiguous
+    T* trow = Tm + (int64_t)t * d;
+    T* told = (T*)h->sp_told + (int64_t)(S.ct & 1) * d;
+    T* ms = (T*)h->mstat;                                            // [numer(d) | denom(d)]
+    launch_sp_pack<T>((const T*)S.csc.wo, (const T*)S.csc.wn, wt, wt, h->sp_quad, n, st);
+    launch_sp_pass<T>(h->csc, h->sp_quad, (const T*)S.csc.to, (const T*)S.csc.tn, trow, told, ms, ms + d, h->sm_count, st);
+    h->launches += 2;
+    if (h->world > 1 && allreduce(h, ms, (size_t)2 * d, st)) return 1;
+    launch_wrri_final<T>(ms, ms + d, 1, d, solve_args(p, true), trow, 1, (T*)h->Tt + t, h->k, h->flags, st);
+    launch_vec_sum_flag<T>(trow, d, 1, h->sums, t, 1, h->flags, st);
+    h->launches += 2;
+    S.csc = SpPending{wt, wt, told, trow};       // w_t (told - tnew)'; merged with the W-step's change if one follows
+    S.told_cur = told;
+    S.ct++;
+    return 0;
+}
+
+template <typename T>
+static int sp_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, SpState& S, cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d;
+    T* wt = (T*)h->Wt + (int64_t)t * h->ldwt;
+    const T* trow = Tm + (int64_t)t * d;
+    const T* told = S.told_cur ? (const T*)S.told_cur : trow;
+    T* wold = (T*)h->sp_wold + (int64_t)(S.cw & 1) * n;
+    T* ms = (T*)h->mstat;                                            // [numer(n) | denom(n)]
+    launch_sp_pack<T>((const T*)S.csr.to, (const T*)S.csr.tn, told, trow, h->sp_quad, d, st);
+    launch_sp_pass<T>(h->csr, h->sp_quad, (const T*)S.csr.wo, (const T*)S.csr.wn, wt, wold, ms, ms + n, h->sm_count, st);
+    launch_wrri_final<T>(ms, ms + n, 1, n, solve_args(p, false), W + t, h->k, wt, 1, h->flags, st);
+    launch_vec_sum_flag<T>(wt, n, 1, h->sums, h->k + t, h->world > 1 ? 0 : 2, h->flags, st);
+    h->launches += 4;
+    if (h->world > 1) {
+        NCK(g_nccl.AllReduce(h->sums + h->k + t, h->sums + h->k + t, 1, 8, 0, h->comm, st));
+        launch_flag_from_sums(h->sums, h->k + t, 1, 2, h->flags, st);
+        h->launches += 2;
+    }
+    // both copies now lag by  wold told' - wnew tnew'  (one record even when a T-step preceded: the terms in
+    // w_old t_new' cancel)
+    S.csr = SpPending{wold, wt, told, trow};
+    if (S.told_cur) S.csc = S.csr;
+    S.told_cur = nullptr;
+    S.cw++;
+    return 0;
+}
+
+template <typename T>
+static int sp_load_factors(rri_handle_t h, const T* W, const T* Tm, cudaStream_t st)
+{
+    launch_transpose<T>(Tm, h->k, h->d, h->d, (T*)h->Tt, h->k, st);          // T' [d,k]
+    launch_transpose<T>(W, h->n, h->k, h->k, (T*)h->Wt, h->ldwt, st);        // W' [k,ldwt]
+    h->launches += 2;
+    CKL();
+    return 0;
+}
+
+template <typename T>
+static int sp_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri_params_t* p, cudaStream_t st)
+{
+    // reference order (nmf.py:415-476); both residual copies restart from the current factors
+    SpState S;
+    sp_refresh<T>(h, false, W, st);
+    sp_refresh<T>(h, true, W, st);
+    for (int t = t0; t < t1; ++t) {
+        if (sp_T_step<T>(h, W, Tm, t, p, S, st)) return 1;
+        if (sp_W_step<T>(h, W, Tm, t, p, S, st)) return 1;
+    }
+    CKL();
+    return 0;
+}
+
+template <typename T>
+static int sp_sweeps(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_params_t* p, cudaStream_t st)
+{
+    const int k = h->k;
+    if (sp_load_factors<T>(h, W, Tm, st)) return 1;
+    for (int s = 0; s < n_sweeps; ++s) {
+        if (!p->fix_T && h->order == RRI_ORDER_RRI) {
+            if (sp_topic_range<T>(h, W, Tm, 0, k, p, st)) return 1;
+            continue;
+        }
+        if (!p->fix_T) {                       // block order, T half: only the column copy is read
+            SpState S;
+            sp_refresh<T>(h, false, W, st);
+            for (int t = 0; t < k; ++t) {
+                if (sp_T_step<T>(h, W, Tm, t, p, S, st)) return 1;
+                S.told_cur = nullptr;
+            }
+        }
+        SpState S;                             // W half (also transform(): fix_T): only the row copy is read
+        sp_refresh<T>(h, true, W, st);
+        for (int t = 0; t < k; ++t)
+            if (sp_W_step<T>(h, W, Tm, t, p, S, st)) return 1;
+    }
+    CKL();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 // sweeps
 // -------------------------------------------------------------------------------------------------
 template <typename T>
@@ -782,6 +975,7 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
 {
     const int k = h->k;
     const int64_t n = h->n, d = h->d;
+    if (h->sparse) return sp_sweeps<T>(h, W, Tm, n_sweeps, p, st);
     if (h->mk != MK_NONE) {
         if (h->wtc) { wrri_tc_load_factors(h->wtc, (const float*)W, (const float*)Tm, st); h->launches += 2; }
         for (int s = 0; s < n_sweeps; ++s) {
@@ -852,6 +1046,10 @@ extern "C" int rri_sweeps(rri_handle_t h, void* W_dev, void* T_dev, int32_t n_sw
 template <typename T>
 static int topics_impl(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri_params_t* p, cudaStream_t st)
 {
+    if (h->sparse) {
+        if (sp_load_factors<T>(h, W, Tm, st)) return 1;
+        return sp_topic_range<T>(h, W, Tm, t0, t1, p, st);
+    }
     if (h->mk != MK_NONE) {
         if (h->wtc) { wrri_tc_load_factors(h->wtc, (const float*)W, (const float*)Tm, st); h->launches += 2; }
         for (int t = t0; t < t1; ++t) {
@@ -901,6 +1099,16 @@ extern "C" int rri_topic_sums(rri_handle_t h, double* sum_T_host, double* sum_W_
 template <typename T>
 static int objective_impl(rri_handle_t h, const T* W, const T* Tm, cudaStream_t st)
 {
+    if (h->sparse) {
+        launch_transpose<T>(Tm, h->k, h->d, h->d, (T*)h->Tt, h->k, st);
+        sp_refresh<T>(h, true, W, st);
+        launch_sp_objective<T>(h->csr, h->nnz, h->obj_part, h->obj_out, st);
+        launch_norms<T>(W, h->n * h->k, h->obj_part, h->obj_out + 2, st);
+        launch_norms<T>(Tm, (int64_t)h->k * h->d, h->obj_part, h->obj_out + 4, st);
+        h->launches += 7;
+        CKL();
+        return 0;
+    }
     launch_objective<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, h->n, h->d, h->k, h->obj_part,
                         h->oblocks, h->obj_out, st);
     launch_norms<T>(W, h->n * h->k, h->obj_part, h->obj_out + 2, st);
@@ -945,6 +1153,16 @@ static int partials_impl(rri_handle_t h, const T* W, const T* Tm, int t, T* wR, 
     const int64_t d = h->d;
     rri_params_t p;
     memset(&p, 0, sizeof(p));
+    if (h->sparse) {
+        if (sp_load_factors<T>(h, W, Tm, st)) return 1;
+        sp_refresh<T>(h, false, W, st);
+        const T* wt = (const T*)h->Wt + (int64_t)t * h->ldwt;
+        launch_sp_pack<T>(nullptr, nullptr, wt, wt, h->sp_quad, h->n, st);
+        launch_sp_pass<T>(h->csc, h->sp_quad, nullptr, nullptr, Tm + (int64_t)t * d, (T*)h->sp_told, wR, nw, h->sm_count, st);
+        h->launches += 2;
+        CKL();
+        return 0;
+    }
     if (h->mk != MK_NONE) {
         launch_wrri_tstats<T>((const T*)h->X, h->ldx, h->M, h->mk, h->ldm, W, Tm, h->n, d, h->k, t,
                               (T*)h->numer_part, (T*)h->denom_part, h->tpl, st);

@@ -106,7 +106,7 @@ namespace rri {
 // ---------------------------------------------------------------------------------------------
 // masked / weighted WRRI half-steps and the objective                      (wrri_kernels.cu)
 // ---------------------------------------------------------------------------------------------
-enum { MK_NONE = 0, MK_REAL = 1, MK_U8 = 2 };
+enum { MK_NONE = 0, MK_REAL = 1, MK_U8 = 2, MK_SPARSE = 3 /* observed entries only: sparse_kernels.cu */ };
 
 struct TilePlan { int tiles_r, tiles_c, groups; };      // groups = partial slices written
 TilePlan plan_tstats(int64_t n, int64_t d, int sm_count);
@@ -158,4 +158,45 @@ void launch_flag_from_sums(const double* sums, int off, int k, int zero_flag, in
 // matrixops.py:5-69 computes the same threshold by sorting)
 template <typename T>
 void launch_project_rows_simplex(T* A, int64_t rows, int64_t cols, double s, cudaStream_t st);
+}  // namespace rri
+
+namespace rri {
+// ---------------------------------------------------------------------------------------------
+// observed-entries (sparse) WRRI: CSR + CSC residual copies                 (sparse_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+struct SpSide {            // one compressed orientation of the observed entries
+    int64_t nseg;          // rows (CSR) or columns (CSC)
+    const int64_t* ptr;    // [nseg + 1]
+    const int32_t* idx;    // [nnz] column (CSR) / row (CSC) of every entry, ascending inside a segment
+    const void* x;         // [nnz] observed values in this order
+    const void* wgt;       // [nnz] entry weights in this order, or null (all ones)
+    void* E;               // [nnz] residual X - W T at the observed entries
+    int group;             // threads that share a segment: 32 (a warp) or 256 (a block)
+};
+
+// Column orientation of a CSR matrix: colptr[d+1], csc_row[nnz], x_csc[nnz] (, w_csc[nnz]); rows ascending inside
+// a column.  Returns 0, a cudaError_t (> 0), or -(bit mask) for a malformed CSR: 1 rowptr, 2 column range,
+// 4 columns not strictly ascending inside a row.  Synchronises `st`.
+template <typename T>
+int sp_build_csc(const int64_t* rowptr, const int32_t* col, const T* x, const T* w, int64_t n, int64_t d,
+                 int64_t nnz, int64_t* colptr, int32_t* csc_row, T* x_csc, T* w_csc, int sm_count, int* err_dev,
+                 cudaStream_t st);
+
+// s.E[p] = s.x[p] - sum_l A[seg,l] * B[s.idx[p],l]   (A: own factor rows [nseg,k], B: other factor rows [.,k])
+template <typename T>
+void launch_sp_residual(const SpSide& s, const T* A, const T* B, int k, int sm_count, cudaStream_t st);
+
+// quad[i] = {po[i], pn[i], vold[i], vnew[i]}   (po/pn null -> 0): the 16/32-byte gather record of a pass
+template <typename T>
+void launch_sp_pack(const T* po, const T* pn, const T* vold, const T* vnew, void* quad, int64_t len, cudaStream_t st);
+
+// One half-step statistic over one orientation (see sparse_kernels.cu): applies the pending rank-one change
+// (own_po/own_pn null -> none), writes numer[seg], denom[seg] (before the regularisers) and own_save[seg] = own_cur[seg].
+template <typename T>
+void launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* own_pn, const T* own_cur,
+                    T* own_save, T* numer, T* denom, int sm_count, cudaStream_t st);
+
+// out[0] = 0.5 * sum m E^2, out[1] = sum m x^2 over the observed entries (fixed-order reduction)
+template <typename T>
+void launch_sp_objective(const SpSide& s, int64_t nnz, double* part, double* out, cudaStream_t st);
 }  // namespace rri

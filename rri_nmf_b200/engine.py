@@ -52,6 +52,8 @@ class RRIEngine(object):
 
     X: torch tensor [n_local, d] on a CUDA device, float32 or float64, row-major (a row stride >= d
     is allowed).  W_mat: optional weights, same shape (same dtype, or uint8 0/1 mask).
+    X may also be a torch sparse CSR tensor: its stored entries are the observed ones (the recommender
+    setting, never densified); W_mat is then an optional 1-D tensor of nnz entry weights.
     order: 'rri' (reference-exact interleaved order, nmf.py:415-476) or 'hals' (block order).
     math : 'ieee' or 'tf32' (tcgen05 tensor-core contraction; float32 + hals only).
     """
@@ -63,7 +65,10 @@ class RRIEngine(object):
             raise ValueError('X must be 2-D')
         if X.dtype not in (torch.float32, torch.float64):
             raise ValueError('X must be float32 or float64')
-        if X.stride(1) != 1:
+        self.sparse = X.layout == torch.sparse_csr
+        if not self.sparse and X.layout != torch.strided:
+            raise ValueError('X must be a dense (strided) or a sparse CSR tensor')
+        if not self.sparse and X.stride(1) != 1:
             X = X.contiguous()
         self.lib = _lib.load()
         self.X = X
@@ -75,6 +80,22 @@ class RRIEngine(object):
         self.math = math
         self.comm = comm
         self.W_mat = None
+        self.Xt = None
+        self.peer_exchange = False
+        self.h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.dev_index = dev_index
+        check(self.lib.rri_create(C.byref(self.h), self.n, self.d, self.k,
+                                  _lib.RRI_F32 if self.dtype == torch.float32 else _lib.RRI_F64,
+                                  {'ieee': _lib.RRI_MATH_IEEE, 'tf32': _lib.RRI_MATH_TF32}[math],
+                                  {'rri': _lib.RRI_ORDER_RRI, 'hals': _lib.RRI_ORDER_HALS}[order],
+                                  dev_index))
+        if comm is not None and comm.world > 1:
+            path = comm.nccl_path.encode() if comm.nccl_path else None
+            check(self.lib.rri_set_comm(self.h, comm.comm, comm.rank, comm.world, path))
+        if self.sparse:
+            self._bind_csr(X, W_mat)
+            return
         mk = _lib.RRI_MASK_NONE
         ldm = 0
         if W_mat is not None:
@@ -92,18 +113,6 @@ class RRIEngine(object):
                 mk = _lib.RRI_MASK_REAL
             self.W_mat = W_mat
             ldm = int(W_mat.stride(0))
-        self.h = C.c_void_p()
-        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self.dev_index = dev_index
-        check(self.lib.rri_create(C.byref(self.h), self.n, self.d, self.k,
-                                  _lib.RRI_F32 if self.dtype == torch.float32 else _lib.RRI_F64,
-                                  {'ieee': _lib.RRI_MATH_IEEE, 'tf32': _lib.RRI_MATH_TF32}[math],
-                                  {'rri': _lib.RRI_ORDER_RRI, 'hals': _lib.RRI_ORDER_HALS}[order],
-                                  dev_index))
-        if comm is not None and comm.world > 1:
-            path = comm.nccl_path.encode() if comm.nccl_path else None
-            check(self.lib.rri_set_comm(self.h, comm.comm, comm.rank, comm.world, path))
-        self.Xt = None
         if order == 'hals' and self.W_mat is None:
             # the transposed copy of X lives in a torch tensor: allocation and release go through the caching
             # allocator instead of a cudaMalloc/cudaFree of a data-sized buffer per engine
@@ -113,10 +122,42 @@ class RRIEngine(object):
             check(self.lib.rri_set_transpose_storage(self.h, _ptr(self.Xt), ldxt))
         check(self.lib.rri_bind(self.h, _ptr(self.X), int(self.X.stride(0)), _ptr(self.W_mat), mk, ldm,
                                 self._stream()))
-        self.peer_exchange = False
         if (comm is not None and comm.world > 1 and order == 'hals' and self.W_mat is None
                 and os.environ.get('RRI_P2P', '1') != '0'):
             self._setup_peer_exchange(comm)
+
+    def _bind_csr(self, X, weights):
+        """Observed-entries binding (rri_bind_csr): X is a torch sparse CSR tensor whose stored entries are the
+        observed ones; `weights` (optional) is a 1-D tensor of nnz entry weights in the order of X.values()."""
+        if self.math != 'ieee':
+            raise ValueError("sparse (observed-entries) data runs with math='ieee'")
+        self.crow = X.crow_indices().to(torch.int64).contiguous()
+        self.col = X.col_indices().to(torch.int32).contiguous()
+        self.val = X.values().contiguous()
+        self.nnz = int(self.val.numel())
+        self.entry_weights = None
+        if weights is not None:
+            if weights.dim() != 1 or int(weights.numel()) != self.nnz:
+                raise ValueError('with sparse X, W_mat is a 1-D tensor of nnz entry weights (the order of X.values())')
+            self.entry_weights = weights.to(device=self.device, dtype=self.dtype).contiguous()
+        check(self.lib.rri_bind_csr(self.h, self.nnz, _ptr(self.crow), _ptr(self.col), _ptr(self.val),
+                                    _ptr(self.entry_weights), self._stream()))
+
+    @staticmethod
+    def csr_tensor(indptr, indices, data, shape, device, dtype=None):
+        """torch sparse CSR tensor on `device` from host or device index/value arrays (the form RRIEngine takes for
+        observed-entries data); the three components are moved one by one, the matrix is never densified."""
+        def dev(a, dt):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            return t.to(device=device, dtype=dt)
+        val = dev(data, dtype)
+        return torch.sparse_csr_tensor(dev(indptr, torch.int64), dev(indices, torch.int64), val,
+                                       size=tuple(int(x) for x in shape), check_invariants=False)
+
+    @property
+    def masked(self):
+        """True when only a subset of the entries is fitted (dense W_mat or sparse observed entries)"""
+        return self.sparse or self.W_mat is not None
 
     def _setup_peer_exchange(self, comm):
         """Map every rank's exchange buffer (CUDA IPC over NVLink) so that the T half-step reads the shard
@@ -233,7 +274,7 @@ class RRIEngine(object):
         """Shard statistic of nmf.py:680-686 / :706-713 for topic t: (wR[d], nw[1 or d])."""
         self._check_factors(W, T)
         wR = torch.empty(self.d, dtype=self.dtype, device=self.device)
-        nw = torch.empty(self.d if self.W_mat is not None else 1, dtype=self.dtype, device=self.device)
+        nw = torch.empty(self.d if self.masked else 1, dtype=self.dtype, device=self.device)
         check(self.lib.rri_partials_T(self.h, _ptr(W), _ptr(T), int(t), _ptr(wR), _ptr(nw), self._stream()))
         return wR, nw
 

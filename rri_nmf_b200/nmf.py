@@ -9,11 +9,16 @@ Additional keyword-only arguments select the device path:
                   'hals' -- block order: all T-steps then all W-steps (2 passes over X per sweep)
     math          'ieee' (default) or 'tf32' (tcgen05 tensor-core contractions; float32 + 'hals')
     comm          engine.NcclComm for a row-sharded multi-GPU run (X, W_in, W_mat are the local shards)
+
+X may also be a scipy.sparse matrix or a torch sparse CSR tensor: its STORED entries are the observed ones (the
+recommender setting of sklearn_interface.py:78-102 without densifying the (i, j, rating) triples and without a
+dense W_mat); W_mat is then None or a sparse matrix of the same structure holding entry weights.
 """
 import logging
 import time
 
 import numpy as np
+import scipy.sparse as sp
 import torch
 
 from . import _lib
@@ -45,6 +50,39 @@ def _universal_stopping_condition(obj_history, eps_stop=1e-4):
 
 def _is_empty(a):
     return a is None or int(np.prod(np.shape(a))) == 0
+
+
+def _is_sparse(X):
+    return sp.issparse(X) or (isinstance(X, torch.Tensor) and X.layout != torch.strided)
+
+
+def _sparse_to_device(X, W_mat, device, dtype):
+    """(torch sparse CSR tensor on `device`, 1-D entry weights or None) from a scipy.sparse matrix or a torch
+    sparse tensor; indices sorted, duplicates summed (what coo_matrix(...).toarray() does in the reference,
+    sklearn_interface.py:78-83)."""
+    if isinstance(X, torch.Tensor):
+        Xc = X.to_sparse_csr() if X.layout != torch.sparse_csr else X
+        Xc = RRIEngine.csr_tensor(Xc.crow_indices(), Xc.col_indices(), Xc.values(), Xc.shape, device, dtype)
+        wts = None
+        if W_mat is not None:
+            if not (isinstance(W_mat, torch.Tensor) and W_mat.dim() == 1):
+                raise ValueError('with a sparse tensor X, W_mat is a 1-D tensor of nnz entry weights')
+            wts = W_mat.to(device=device, dtype=dtype)
+        return Xc, wts
+    Xs = X.tocsr(copy=True)
+    Xs.sum_duplicates()
+    Xs.sort_indices()
+    wts = None
+    if W_mat is not None:
+        if not sp.issparse(W_mat):
+            raise ValueError('with sparse X, W_mat must be a sparse matrix with the structure of X (entry weights)')
+        Ms = W_mat.tocsr(copy=True)
+        Ms.sum_duplicates()
+        Ms.sort_indices()
+        if Ms.shape != Xs.shape or not (np.array_equal(Ms.indptr, Xs.indptr) and np.array_equal(Ms.indices, Xs.indices)):
+            raise ValueError('sparse W_mat must store exactly the entries X stores')
+        wts = torch.from_numpy(np.ascontiguousarray(Ms.data)).to(device=device, dtype=dtype)
+    return RRIEngine.csr_tensor(Xs.indptr, Xs.indices, Xs.data, Xs.shape, device, dtype), wts
 
 
 def _to_device(a, device, dtype):
@@ -126,17 +164,32 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         raise _lib.RriError('rri_nmf_b200.nmf runs on CUDA devices only (no CPU fallback)')
     if device.index is None:
         device = torch.device('cuda', torch.cuda.current_device())
+    sparse_in = _is_sparse(X)
     if isinstance(X, torch.Tensor):
         dtype = X.dtype if X.dtype in (torch.float32, torch.float64) else torch.float64
     else:
-        dtype = torch.float32 if np.asarray(X).dtype == np.float32 else torch.float64
+        dtype = torch.float32 if (X.dtype if sparse_in else np.asarray(X).dtype) == np.float32 else torch.float64
 
     # ---- initialisation and validation, as nmf.py:819-880
     if _is_empty(W_in) or _is_empty(T_in):
-        Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
-        Mh = None
-        if W_mat is not None:
-            Mh = W_mat.detach().cpu().numpy() if isinstance(W_mat, torch.Tensor) else np.asarray(W_mat)
+        if sparse_in:
+            # M o X is the sparse matrix itself (entry weights folded in): the SVD never densifies it
+            if isinstance(X, torch.Tensor):
+                Xc = X.detach().to_sparse_csr().cpu()
+                Xh = sp.csr_matrix((Xc.values().numpy(), Xc.col_indices().numpy(), Xc.crow_indices().numpy()),
+                                   shape=(n, d))
+                if W_mat is not None:
+                    Xh.data = Xh.data * W_mat.detach().cpu().numpy()
+            else:
+                Xh = X.tocsr()
+                if W_mat is not None:
+                    Xh = Xh.multiply(W_mat).tocsr()
+            Mh = None
+        else:
+            Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
+            Mh = None
+            if W_mat is not None:
+                Mh = W_mat.detach().cpu().numpy() if isinstance(W_mat, torch.Tensor) else np.asarray(W_mat)
         W0, T0 = initialize_nmf(Mh * Xh if Mh is not None else Xh, k, init, random_state=random_state,
                                 row_normalize=False)
         if t_row_sum is not None:
@@ -154,7 +207,10 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
     timing = {}
     _t0 = time.perf_counter()
     with torch.cuda.device(device):
-        Xd = _to_device(X, device, dtype)
+        if sparse_in:
+            Xd, W_mat = _sparse_to_device(X, W_mat, device, dtype)
+        else:
+            Xd = _to_device(X, device, dtype)
         # np.maximum(W_in, 0) makes copies: the caller's arrays are never mutated (nmf.py:867-868)
         W = _to_device(W0, device, dtype).clamp(min=0).contiguous()
         T = _to_device(T0, device, dtype).clamp(min=0).contiguous()
@@ -163,7 +219,9 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
             T = T.clone()
         Md = None
-        if W_mat is not None:
+        if sparse_in:
+            Md = W_mat                          # 1-D entry weights (or None), already on the device
+        elif W_mat is not None:
             if isinstance(W_mat, torch.Tensor) and W_mat.dtype in (torch.uint8, torch.bool):
                 Md = W_mat.to(device)
             else:
@@ -180,7 +238,7 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         keep = False
         try:
             _t2 = time.perf_counter()
-            out = _solve(engine, Xd, W, T, rtv, locals())
+            out = _solve(engine, X if sparse_in else Xd, W, T, rtv, locals())
             timing['solve_s'] = time.perf_counter() - _t2           # (rest of the H2D copy,) sweeps, device -> host copy of W, T
             out['timing'] = timing
             keep = 'obj_calculator' in out        # the returned objective calculator owns the engine
@@ -212,12 +270,14 @@ def _solve(engine, Xd, W, T, rtv, a):
 
     params = engine.params(ub_w=w_row_sum, ub_t=t_row_sum, fix_T=fix_T,
                            simplex_T=bool(project_T_each_iter and t_row_sum and not fix_T), **regs)
-    masked = engine.W_mat is not None
+    masked = engine.masked
 
     def host_view(t):
         return t.detach().cpu().numpy() if numpy_io else t
 
-    Xcb = host_view(Xd) if (callable(early_stop) or diagnostics) else None
+    Xcb = None
+    if callable(early_stop) or diagnostics:
+        Xcb = Xd if a['sparse_in'] else host_view(Xd)          # sparse input is handed to callbacks as given
     state = {'n_resets_remaining': a['n_resets']}
     iter_cputime = []
     obj_history = []

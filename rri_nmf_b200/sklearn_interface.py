@@ -4,7 +4,9 @@ parameters, methods and attributes (`W`, `T`, `nmf_outputs`, `idf`, `min_rating`
 plus the sklearn-conventional read-only aliases `components_` (= T), `n_components` (= k) and
 `reconstruction_err_` that BASELINE.json's north_star asks for.
 
-Additional constructor arguments: `device`, `update_order`, `math` (forwarded to `nmf`).
+Additional constructor arguments: `device`, `update_order`, `math` (forwarded to `nmf`); `NMF_RS_Estimator` also
+takes `sparse=True` to keep the (i, j, rating) triples sparse all the way to the device (observed-entries engine,
+traffic proportional to the number of ratings) instead of densifying them as the reference does.
 """
 import numpy as np
 import scipy.sparse as sp
@@ -145,7 +147,7 @@ class NMF_RS_Estimator(_FactorMixin, sklearn.base.BaseEstimator):
     (sklearn_interface.py:14-182)."""
 
     def __init__(self, n, d, k, wr1=0, tr1=0, random_state=0, W=_EMPTY, T=_EMPTY, max_iter=30, nmf_kwargs={},
-                 use_validation_early_stopping=True, device=None, update_order='rri', math='ieee'):
+                 use_validation_early_stopping=True, device=None, update_order='rri', math='ieee', sparse=False):
         self.n, self.d, self.k = n, d, k
         self.max_iter = max_iter
         self.wr1, self.tr1 = wr1, tr1
@@ -157,6 +159,16 @@ class NMF_RS_Estimator(_FactorMixin, sklearn.base.BaseEstimator):
         self.W, self.T = W, T
         self.nmf_kwargs = nmf_kwargs
         self.device, self.update_order, self.math = device, update_order, math
+        self.sparse = sparse
+
+    def _observed(self, ij, r):
+        """n*d matrix of the ratings: duplicates summed, zero ratings unobserved -- what
+        coo_matrix(...).toarray() followed by `Xtr != 0` gives in the reference (sklearn_interface.py:78-83, :100-102)"""
+        M = sp.coo_matrix((np.asarray(r, dtype=np.float64), (ij[:, 0], ij[:, 1])), shape=(self.n, self.d)).tocsr()
+        M.sum_duplicates()
+        M.eliminate_zeros()
+        M.sort_indices()
+        return M
 
     def fit(self, X, y=None):
         """X: (m, 2) integer (i, j) pairs; y: (m,) ratings (sklearn_interface.py:59-128)"""
@@ -165,10 +177,10 @@ class NMF_RS_Estimator(_FactorMixin, sklearn.base.BaseEstimator):
         self.min_rating, self.max_rating = np.min(y), np.max(y)
         if self.use_validation_early_stopping:
             UItr, UIval, Rtr, Rval = train_test_split(X, y, test_size=0.05, random_state=0, stratify=None)
-            Xtr = sp.coo_matrix((Rtr, (UItr[:, 0], UItr[:, 1])), shape=(self.n, self.d)).toarray()
-            Xv = sp.coo_matrix((Rval, (UIval[:, 0], UIval[:, 1])), shape=(self.n, self.d)).toarray()
+            Xtr = self._observed(UItr, Rtr)
+            Xv = self._observed(UIval, Rval)
             Iv, Jv = Xv.nonzero()
-            held = Xv[Iv, Jv]
+            held = np.asarray(Xv[Iv, Jv]).ravel()
             lo, hi = float(self.min_rating), float(self.max_rating)
 
             def RMSE_val(Xign, W, T):
@@ -186,23 +198,27 @@ class NMF_RS_Estimator(_FactorMixin, sklearn.base.BaseEstimator):
             self.early_stop = RMSE_val
         else:
             self.early_stop = False
-            Xtr = sp.coo_matrix((y, (X[:, 0], X[:, 1])), shape=(self.n, self.d)).toarray()
-        Xtr = Xtr.astype(np.float64)
-        W_mat_tr = (Xtr != 0).astype(np.uint8)                      # sklearn_interface.py:100-102
+            Xtr = self._observed(X, y)
         W_in, T_in = self._warm_start()
         kw = dict(self._device_kwargs())
         kw.update(self.nmf_kwargs)
-        soln = nmf(Xtr, self.k, max_iter=self.max_iter, max_time=7200, compute_obj_each_iter=True,
+        if self.sparse:
+            data, W_mat_tr = Xtr, None                                # stored entries = observed entries
+        else:
+            data = Xtr.toarray()
+            W_mat_tr = torch.from_numpy((data != 0).astype(np.uint8))   # sklearn_interface.py:100-102
+        soln = nmf(data, self.k, max_iter=self.max_iter, max_time=7200, compute_obj_each_iter=True,
                    reset_topic_method=None, early_stop=self.early_stop, project_T_each_iter=False,
                    t_row_sum=1.0, project_W_each_iter=False, w_row_sum=None,
-                   W_mat=torch.from_numpy(W_mat_tr), W_in=W_in, T_in=T_in, reg_w_l1=self.wr1,
+                   W_mat=W_mat_tr, W_in=W_in, T_in=T_in, reg_w_l1=self.wr1,
                    reg_t_l1=self.tr1, random_state=self.random_state, **kw)   # sklearn_interface.py:116-123
         self.W = soln.pop('W')
         self.T = soln.pop('T')
         self.nmf_outputs = soln
         self.Xpred = _EMPTY
         I, J = Xtr.nonzero()
-        self._reconstruction_err = float(np.sqrt((((self.W.dot(self.T))[I, J] - Xtr[I, J]) ** 2).sum()))
+        pred = np.einsum('ik,ki->i', self.W[I, :], self.T[:, J])
+        self._reconstruction_err = float(np.sqrt(((pred - np.asarray(Xtr[I, J]).ravel()) ** 2).sum()))
         return self
 
     def fit_from_Xtr(self, Xtr):
@@ -213,8 +229,13 @@ class NMF_RS_Estimator(_FactorMixin, sklearn.base.BaseEstimator):
 
     def transform(self, Xnew):
         """express Xnew in terms of the fitted topics (sklearn_interface.py:144-156)"""
-        Xnew = np.asarray(Xnew.toarray() if sp.issparse(Xnew) else Xnew, dtype=np.float64)
-        mask = torch.from_numpy((Xnew != 0).astype(np.uint8))
+        if self.sparse:
+            Xnew = sp.csr_matrix(Xnew, dtype=np.float64)
+            Xnew.eliminate_zeros()
+            mask = None
+        else:
+            Xnew = np.asarray(Xnew.toarray() if sp.issparse(Xnew) else Xnew, dtype=np.float64)
+            mask = torch.from_numpy((Xnew != 0).astype(np.uint8))
         soln = nmf(Xnew, self.k, max_iter=4, max_time=7200, project_W_each_iter=False,
                    project_T_each_iter=False, W_mat=mask, T_in=self.T, fix_T=True, reg_w_l1=self.wr1,
                    reg_t_l1=self.tr1, t_row_sum=1.0, w_row_sum=None, reset_topic_method='random',
