@@ -147,6 +147,7 @@ struct rri_handle_s {
     void *sp_quad = nullptr;           // [max(n,d)] packed gather records of one pass
     void *sp_told = nullptr;           // [2][d] T[t,:] before its T-step (two topics in flight)
     void *sp_wold = nullptr;           // [2][n] W[:,t] before its W-step
+    void *sp_npart = nullptr, *sp_dpart = nullptr;     // per-block partial sums of a pass: [nblk][nseg] each
     int* sp_err = nullptr;
     // common
     double* sums = nullptr;    // [2k] device
@@ -542,9 +543,30 @@ static int bind_csr_impl(rri_handle_t h, const int64_t* rowptr, const int32_t* c
                     (-rc & 2) ? " column index outside [0,d);" : "",
                     (-rc & 4) ? " column indices must be strictly ascending inside every row (sort and merge duplicates);" : "");
     if (rc > 0) return fail("building the column orientation failed: %s", cudaGetErrorString((cudaError_t)rc));
-    h->csr = SpSide{n, rowptr, col, val, wgt, E_csr, nnz / n >= 512 ? 256 : 32};
-    h->csc = SpSide{d, (const int64_t*)colptr, (const int32_t*)csc_row, x_csc, w_csc, E_csc, nnz / d >= 512 ? 256 : 32};
+    h->csr = SpSide{n, rowptr, col, val, wgt, E_csr, nnz / n >= 512 ? 256 : 32, nullptr, 1, 0, d};
+    h->csc = SpSide{d, (const int64_t*)colptr, (const int32_t*)csc_row, x_csc, w_csc, E_csc, nnz / d >= 512 ? 256 : 32,
+                    nullptr, 1, 0, n};
     h->launches += 8;
+    // blocked passes: the gathered factor is staged through shared memory in blocks of nb records
+    const char* env = getenv("RRI_SP_BLOCKED");
+    const bool blocked = !(env && *env == '0');
+    const int nb = sp_block_len((int)es);
+    size_t part_elems = (size_t)m;
+    for (SpSide* sd : {&h->csr, &h->csc}) {
+        const int64_t nblk = (sd->nother + nb - 1) / nb;
+        if (!blocked || nblk > 64) continue;          // (a very long factor would make the sub-segments too short)
+        void* p2 = nullptr;
+        if (ws_alloc(h, &p2, sizeof(int64_t) * (size_t)sd->nseg * (size_t)(nblk + 1))) return 1;
+        CK(cudaStreamSynchronize(0));
+        launch_sp_subptr(sd->ptr, sd->idx, sd->nseg, (int)nblk, nb, (int64_t*)p2, h->sm_count, st);
+        sd->ptr2 = (const int64_t*)p2; sd->nblk = (int)nblk; sd->nb = nb;
+        if ((size_t)nblk * (size_t)sd->nseg > part_elems) part_elems = (size_t)nblk * (size_t)sd->nseg;
+        h->launches++;
+    }
+    if (ws_alloc(h, &h->sp_npart, es * part_elems) || ws_alloc(h, &h->sp_dpart, es * part_elems)) return 1;
+    CK(cudaStreamSynchronize(0));
+    CKL();
+    CK(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -873,12 +895,20 @@ static int sp_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
     const T* wt = (const T*)h->Wt + (int64_t)t * h->ldwt;            // W[:,t], contiguous
     T* trow = Tm + (int64_t)t * d;
     T* told = (T*)h->sp_told + (int64_t)(S.ct & 1) * d;
-    T* ms = (T*)h->mstat;                                            // [numer(d) | denom(d)]
+    T* ms = (T*)h->mstat;                                            // [numer(d) | denom(d)] for the all-reduce
     launch_sp_pack<T>((const T*)S.csc.wo, (const T*)S.csc.wn, wt, wt, h->sp_quad, n, st);
-    launch_sp_pass<T>(h->csc, h->sp_quad, (const T*)S.csc.to, (const T*)S.csc.tn, trow, told, ms, ms + d, h->sm_count, st);
+    const T* nu = (const T*)h->sp_npart; const T* de = (const T*)h->sp_dpart;
+    int parts = launch_sp_pass<T>(h->csc, h->sp_quad, (const T*)S.csc.to, (const T*)S.csc.tn, trow, told, (T*)h->sp_npart,
+                                  (T*)h->sp_dpart, h->sm_count, st);
     h->launches += 2;
-    if (h->world > 1 && allreduce(h, ms, (size_t)2 * d, st)) return 1;
-    launch_wrri_final<T>(ms, ms + d, 1, d, solve_args(p, true), trow, 1, (T*)h->Tt + t, h->k, h->flags, st);
+    if (h->world > 1) {
+        launch_reduce_parts<T>(nu, parts, d, d, ms, st);
+        launch_reduce_parts<T>(de, parts, d, d, ms + d, st);
+        h->launches += 2;
+        if (allreduce(h, ms, (size_t)2 * d, st)) return 1;
+        nu = ms; de = ms + d; parts = 1;
+    }
+    launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), trow, 1, (T*)h->Tt + t, h->k, h->flags, st);
     launch_vec_sum_flag<T>(trow, d, 1, h->sums, t, 1, h->flags, st);
     h->launches += 2;
     S.csc = SpPending{wt, wt, told, trow};       // w_t (told - tnew)'; merged with the W-step's change if one follows
@@ -895,10 +925,11 @@ static int sp_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
     const T* trow = Tm + (int64_t)t * d;
     const T* told = S.told_cur ? (const T*)S.told_cur : trow;
     T* wold = (T*)h->sp_wold + (int64_t)(S.cw & 1) * n;
-    T* ms = (T*)h->mstat;                                            // [numer(n) | denom(n)]
     launch_sp_pack<T>((const T*)S.csr.to, (const T*)S.csr.tn, told, trow, h->sp_quad, d, st);
-    launch_sp_pass<T>(h->csr, h->sp_quad, (const T*)S.csr.wo, (const T*)S.csr.wn, wt, wold, ms, ms + n, h->sm_count, st);
-    launch_wrri_final<T>(ms, ms + n, 1, n, solve_args(p, false), W + t, h->k, wt, 1, h->flags, st);
+    const int parts = launch_sp_pass<T>(h->csr, h->sp_quad, (const T*)S.csr.wo, (const T*)S.csr.wn, wt, wold,
+                                        (T*)h->sp_npart, (T*)h->sp_dpart, h->sm_count, st);
+    launch_wrri_final<T>((const T*)h->sp_npart, (const T*)h->sp_dpart, parts, n, solve_args(p, false), W + t, h->k, wt, 1,
+                         h->flags, st);
     launch_vec_sum_flag<T>(wt, n, 1, h->sums, h->k + t, h->world > 1 ? 0 : 2, h->flags, st);
     h->launches += 4;
     if (h->world > 1) {
@@ -1158,8 +1189,11 @@ static int partials_impl(rri_handle_t h, const T* W, const T* Tm, int t, T* wR, 
         sp_refresh<T>(h, false, W, st);
         const T* wt = (const T*)h->Wt + (int64_t)t * h->ldwt;
         launch_sp_pack<T>(nullptr, nullptr, wt, wt, h->sp_quad, h->n, st);
-        launch_sp_pass<T>(h->csc, h->sp_quad, nullptr, nullptr, Tm + (int64_t)t * d, (T*)h->sp_told, wR, nw, h->sm_count, st);
-        h->launches += 2;
+        const int parts = launch_sp_pass<T>(h->csc, h->sp_quad, nullptr, nullptr, Tm + (int64_t)t * d, (T*)h->sp_told,
+                                            (T*)h->sp_npart, (T*)h->sp_dpart, h->sm_count, st);
+        launch_reduce_parts<T>((const T*)h->sp_npart, parts, d, d, wR, st);
+        launch_reduce_parts<T>((const T*)h->sp_dpart, parts, d, d, nw, st);
+        h->launches += 4;
         CKL();
         return 0;
     }

@@ -172,7 +172,14 @@ struct SpSide {            // one compressed orientation of the observed entries
     const void* wgt;       // [nnz] entry weights in this order, or null (all ones)
     void* E;               // [nnz] residual X - W T at the observed entries
     int group;             // threads that share a segment: 32 (a warp) or 256 (a block)
+    // blocked passes (optional): the other factor's index range cut into nblk blocks of nb records
+    const int64_t* ptr2;   // [nseg][nblk + 1] first entry of segment s with index >= b * nb, or null
+    int nblk, nb;
+    int64_t nother;        // length of the other factor's index range (d for CSR, n for CSC)
 };
+int sp_block_len(int elem_size);
+void launch_sp_subptr(const int64_t* ptr, const int32_t* idx, int64_t nseg, int nblk, int nb, int64_t* ptr2,
+                      int sm_count, cudaStream_t st);
 
 // Column orientation of a CSR matrix: colptr[d+1], csc_row[nnz], x_csc[nnz] (, w_csc[nnz]); rows ascending inside
 // a column.  Returns 0, a cudaError_t (> 0), or -(bit mask) for a malformed CSR: 1 rowptr, 2 column range,
@@ -191,9 +198,10 @@ template <typename T>
 void launch_sp_pack(const T* po, const T* pn, const T* vold, const T* vnew, void* quad, int64_t len, cudaStream_t st);
 
 // One half-step statistic over one orientation (see sparse_kernels.cu): applies the pending rank-one change
-// (own_po/own_pn null -> none), writes numer[seg], denom[seg] (before the regularisers) and own_save[seg] = own_cur[seg].
+// (own_po/own_pn null -> none), writes own_save[seg] = own_cur[seg] and `parts` slices numer[p][seg], denom[p][seg]
+// (before the regularisers; the consumer adds the slices in order).  Returns parts (1, or s.nblk when blocked).
 template <typename T>
-void launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* own_pn, const T* own_cur,
+int launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* own_pn, const T* own_cur,
                     T* own_save, T* numer, T* denom, int sm_count, cudaStream_t st);
 
 // out[0] = 0.5 * sum m E^2, out[1] = sum m x^2 over the observed entries (fixed-order reduction)

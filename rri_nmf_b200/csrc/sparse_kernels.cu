@@ -12,6 +12,7 @@
 // rebuilt from X, W, T at the start of every sweep (so N sweeps == N x 1 sweep bit for bit, and rounding drift
 // cannot accumulate).  No atomics: one warp (or one block) owns a whole segment.
 #include <cub/device/device_radix_sort.cuh>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -184,9 +185,77 @@ static void residual_dispatch(const SpSide& s, const T* A, const T* B, int k, in
     }
 }
 
+// Staged variant: a warp copies the k-vectors of 32 entries into shared memory with coalesced row reads (two
+// 128-byte lines per entry at k = 50) and every lane then runs the same fma chain as above on its own entry out of
+// shared memory (row stride odd: conflict-free).  The direct kernel pays one L1 tag look-up per lane and k-chunk
+// (32 distinct lines per warp load) and is bound by that; results are bit-identical.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sp_residual_staged_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const T* __restrict__ x,
+                          const T* __restrict__ A, const T* __restrict__ B, int k, T* __restrict__ E, int64_t nseg,
+                          int ld, int wpb)
+{
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp >= wpb) return;
+    T* __restrict__ tile = reinterpret_cast<T*>(sp_smem) + (size_t)warp * 32 * ld;
+    constexpr int JB = 8;
+    for (int64_t s = (int64_t)blockIdx.x * wpb + warp; s < nseg; s += (int64_t)gridDim.x * wpb) {
+        const int64_t b = ptr[s], e = ptr[s + 1];
+        const T* __restrict__ a = A + s * k;
+        for (int64_t p0 = b; p0 < e; p0 += 32) {
+            const int64_t p = p0 + lane;
+            const bool ok = p < e;
+            const int32_t myidx = ok ? idx[p] : 0;
+            T acc = ok ? x[p] : T(0);
+            const int cnt = (int)((e - p0) < 32 ? (e - p0) : 32);
+            __syncwarp();                                  // the previous tile has been consumed
+            for (int lc = 0; lc < k; lc += 32) {
+                const int l = lc + lane;
+                for (int j0 = 0; j0 < cnt; j0 += JB) {     // loads batched ahead of the shared-memory stores
+                    T v[JB];
+#pragma unroll
+                    for (int u = 0; u < JB; ++u) {
+                        const int64_t r = __shfl_sync(0xffffffffu, myidx, (j0 + u) & 31);
+                        v[u] = (j0 + u < cnt && l < k) ? B[r * k + l] : T(0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < JB; ++u)
+                        if (j0 + u < cnt && l < k) tile[(j0 + u) * ld + l] = v[u];
+                }
+            }
+            __syncwarp();
+            if (ok) {
+                const T* __restrict__ row = tile + lane * ld;
+#pragma unroll 4
+                for (int l = 0; l < k; ++l) acc = fma(-a[l], row[l], acc);
+                E[p] = acc;
+            }
+        }
+    }
+}
+
+static int env_flag(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 template <typename T>
 void launch_sp_residual(const SpSide& s, const T* A, const T* B, int k, int sm_count, cudaStream_t st)
 {
+    static const int staged = env_flag("RRI_SP_RESID_STAGED", 1);
+    if (staged) {
+        const int ld = k | 1;
+        const size_t per_warp = (size_t)32 * ld * sizeof(T);
+        int wpb = (int)((size_t)48 * 1024 / per_warp);
+        if (wpb > 8) wpb = 8;
+        if (wpb >= 1) {
+            sp_residual_staged_kernel<T><<<cap_blocks((s.nseg + wpb - 1) / wpb, sm_count, 4), wpb * 32, wpb * per_warp, st>>>(
+                s.ptr, s.idx, (const T*)s.x, A, B, k, (T*)s.E, s.nseg, ld, wpb);
+            return;
+        }
+    }
     const uintptr_t al = reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B);
     constexpr int VMAX = 16 / (int)sizeof(T);
     if (VMAX == 4 && k % 4 == 0 && (al & 15) == 0) residual_dispatch<T, VMAX>(s, A, B, k, sm_count, st);
@@ -295,13 +364,113 @@ sp_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
     }
 }
 
+// Blocked variant.  The direct kernel above is bound by the gather: 32 lanes hit 32 different 128-byte lines of Q,
+// one L1 tag look-up each (measured 0.38-0.68 ms per pass at 1e8 entries, against 0.12-0.18 ms of HBM time).  Here
+// the index range of the gathered factor is cut into blocks of `nb` records that fit shared memory; CTA (b, c)
+// stages block b of Q once and walks the sub-segments [ptr2[s][b], ptr2[s][b+1]) of its chunk c of the segments, a
+// warp per sub-segment, so every gather is a shared-memory read.  Per-block partial sums are written to
+// numer_part[b][s], denom_part[b][s] and added in block order by the solve kernel (deterministic).
+template <typename T, bool HASW, int U>
+__global__ void __launch_bounds__(1024, 1)
+sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restrict__ idx, T* __restrict__ E,
+                       const T* __restrict__ wgt, const Quad<T>* __restrict__ Q, const T* __restrict__ own_po,
+                       const T* __restrict__ own_pn, const T* __restrict__ own_cur, T* __restrict__ own_save,
+                       T* __restrict__ numer_part, T* __restrict__ denom_part, int64_t nseg, int nblk, int nb,
+                       int64_t nother, int chunks)
+{
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    Quad<T>* __restrict__ qs = reinterpret_cast<Quad<T>*>(sp_smem);
+    const int b = (int)(blockIdx.x % (unsigned)nblk), c = (int)(blockIdx.x / (unsigned)nblk);
+    const int64_t base = (int64_t)b * nb;
+    const int cnt = (int)((nother - base) < (int64_t)nb ? (nother - base) : (int64_t)nb);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) qs[i] = Q[base + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int64_t s0, s1;
+    part_range(nseg, chunks, c, s0, s1);
+    const bool apply = own_po != nullptr;
+    const int32_t ibase = (int32_t)base;
+    const int64_t pstride = (int64_t)nblk + 1;
+    for (int64_t s = s0 + warp; s < s1; s += nwarps) {
+        const int64_t beg = ptr2[s * pstride + b], end = ptr2[s * pstride + b + 1];
+        const T opo = apply ? own_po[s] : T(0), opn = apply ? own_pn[s] : T(0);
+        const T oc = own_cur[s];
+        T num = T(0), den = T(0);
+        for (int64_t p0 = beg + lane; p0 < end + lane; p0 += 32 * U) {        // (p0 - lane) < end: uniform per warp
+            int32_t q[U]; T ev[U]; T m[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t p = p0 + u * 32;
+                const bool ok = p < end;
+                q[u] = ok ? idx[p] - ibase : -1;
+                ev[u] = ok ? E[p] : T(0);
+                m[u] = (HASW && ok) ? wgt[p] : T(1);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (q[u] >= 0) {
+                    const Quad<T> qq = qs[q[u]];
+                    sp_entry<T, HASW>(ev[u], qq, m[u], opo, opn, oc, apply, E + p0 + u * 32, num, den);
+                }
+        }
+        num = warp_sum(num);
+        den = warp_sum(den);
+        if (lane == 0) {
+            numer_part[(int64_t)b * nseg + s] = num;
+            denom_part[(int64_t)b * nseg + s] = den;
+            if (b == 0) own_save[s] = oc;
+        }
+    }
+}
+
+// ptr2[s][b] = first entry of segment s whose index is >= b * nb   (b = 0..nblk)
+__global__ void sp_subptr_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nseg, int nblk,
+                                 int nb, int64_t* __restrict__ ptr2)
+{
+    const int64_t total = nseg * ((int64_t)nblk + 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = i / (nblk + 1);
+        const int b = (int)(i - s * (nblk + 1));
+        int64_t lo = ptr[s], hi = ptr[s + 1];
+        const int64_t target = (int64_t)b * nb;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)idx[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        ptr2[i] = lo;
+    }
+}
+
+int sp_block_len(int elem_size) { return (128 * 1024) / (4 * elem_size); }      // records per staged block of Q
+
+void launch_sp_subptr(const int64_t* ptr, const int32_t* idx, int64_t nseg, int nblk, int nb, int64_t* ptr2,
+                      int sm_count, cudaStream_t st)
+{
+    const int64_t total = nseg * ((int64_t)nblk + 1);
+    sp_subptr_kernel<<<cap_blocks((total + 255) / 256, sm_count, 8), 256, 0, st>>>(ptr, idx, nseg, nblk, nb, ptr2);
+}
+
 template <typename T>
-void launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* own_pn, const T* own_cur,
-                    T* own_save, T* numer, T* denom, int sm_count, cudaStream_t st)
+int launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* own_pn, const T* own_cur,
+                   T* own_save, T* numer, T* denom, int sm_count, cudaStream_t st)
 {
     const Quad<T>* Q = (const Quad<T>*)quad;
     const T* w = (const T*)s.wgt;
     T* E = (T*)s.E;
+    if (s.ptr2) {
+        constexpr int U = sizeof(T) == 8 ? 4 : 8;
+        const int64_t cnt = s.nother < (int64_t)s.nb ? s.nother : (int64_t)s.nb;
+        const size_t smem = (size_t)cnt * sizeof(Quad<T>);
+        int chunks = sm_count / s.nblk;
+        if (chunks < 1) chunks = 1;
+        if ((int64_t)chunks * 32 > s.nseg) chunks = (int)((s.nseg + 31) / 32);
+        if (chunks < 1) chunks = 1;
+        auto kern = w ? sp_pass_blocked_kernel<T, true, U> : sp_pass_blocked_kernel<T, false, U>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        kern<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx, E, w, Q, own_po, own_pn, own_cur, own_save, numer,
+                                                             denom, s.nseg, s.nblk, s.nb, s.nother, chunks);
+        return s.nblk;
+    }
     if (s.group == 256) {
         const int nb = cap_blocks(s.nseg, sm_count, 8);
         if (w) sp_pass_kernel<T, 256, true><<<nb, 256, 0, st>>>(s.ptr, s.idx, E, w, Q, own_po, own_pn, own_cur, own_save, numer, denom, s.nseg);
@@ -311,6 +480,7 @@ void launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T*
         if (w) sp_pass_kernel<T, 32, true><<<nb, 256, 0, st>>>(s.ptr, s.idx, E, w, Q, own_po, own_pn, own_cur, own_save, numer, denom, s.nseg);
         else   sp_pass_kernel<T, 32, false><<<nb, 256, 0, st>>>(s.ptr, s.idx, E, w, Q, own_po, own_pn, own_cur, own_save, numer, denom, s.nseg);
     }
+    return 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -363,8 +533,8 @@ void launch_sp_objective(const SpSide& s, int64_t nnz, double* part, double* out
                                  int64_t*, int32_t*, T*, T*, int, int*, cudaStream_t);                             \
     template void launch_sp_residual<T>(const SpSide&, const T*, const T*, int, int, cudaStream_t);                \
     template void launch_sp_pack<T>(const T*, const T*, const T*, const T*, void*, int64_t, cudaStream_t);         \
-    template void launch_sp_pass<T>(const SpSide&, const void*, const T*, const T*, const T*, T*, T*, T*, int,     \
-                                    cudaStream_t);                                                                 \
+    template int launch_sp_pass<T>(const SpSide&, const void*, const T*, const T*, const T*, T*, T*, T*, int,      \
+                                   cudaStream_t);                                                                  \
     template void launch_sp_objective<T>(const SpSide&, int64_t, double*, double*, cudaStream_t);
 RRI_INST(float)
 RRI_INST(double)
