@@ -148,6 +148,9 @@ struct rri_handle_s {
     void *sp_told = nullptr;           // [2][d] T[t,:] before its T-step (two topics in flight)
     void *sp_wold = nullptr;           // [2][n] W[:,t] before its W-step
     void *sp_npart = nullptr, *sp_dpart = nullptr;     // per-block partial sums of a pass: [nblk][nseg] each
+    uint32_t* sp_perm = nullptr;       // [nnz] CSR position of every CSC entry
+    int sp_ldt = 0;                    // row stride of T' [d, sp_ldt] (k rounded up to 16 bytes: vector gathers)
+    bool sp_refresh_v2 = true;         // residual restart: row copy from the factors, column copy gathered from it
     int* sp_err = nullptr;
     // common
     double* sums = nullptr;    // [2k] device
@@ -534,10 +537,17 @@ static int bind_csr_impl(rri_handle_t h, const int64_t* rowptr, const int32_t* c
         const int64_t v = 16 / (int64_t)es;
         h->ldwt = (n + v - 1) / v * v;
     }
-    if (ws_alloc(h, &h->Wt, es * (size_t)k * h->ldwt) || ws_alloc(h, &h->Tt, es * (size_t)d * k)) return 1;
+    {
+        const char* env = getenv("RRI_SP_REFRESH_V2");
+        h->sp_refresh_v2 = !(env && *env == '0');
+        const int v = 16 / (int)es;
+        h->sp_ldt = h->sp_refresh_v2 ? (k + v - 1) / v * v : k;
+    }
+    if (ws_alloc(h, &h->Wt, es * (size_t)k * h->ldwt) || ws_alloc(h, &h->Tt, es * (size_t)d * h->sp_ldt)) return 1;
+    if (ws_alloc(h, (void**)&h->sp_perm, sizeof(uint32_t) * ne)) return 1;
     CK(cudaStreamSynchronize(0));          // the zero-fills above ran on the legacy default stream
     const int rc = sp_build_csc<T>(rowptr, col, val, wgt, n, d, nnz, (int64_t*)colptr, (int32_t*)csc_row, (T*)x_csc,
-                                   (T*)w_csc, h->sm_count, h->sp_err, st);
+                                   (T*)w_csc, h->sp_perm, h->sm_count, h->sp_err, st);
     if (rc < 0)
         return fail("malformed CSR input:%s%s%s", (-rc & 1) ? " rowptr is not a monotone [0..nnz] sequence;" : "",
                     (-rc & 2) ? " column index outside [0,d);" : "",
@@ -880,12 +890,21 @@ struct SpState {
 };
 
 template <typename T>
-static void sp_refresh(rri_handle_t h, bool csr, const T* W, cudaStream_t st)
+static void sp_refresh(rri_handle_t h, bool need_csr, bool need_csc, const T* W, cudaStream_t st)
 {
     // E = X - W T on the observed entries, from the current factors
-    if (csr) launch_sp_residual<T>(h->csr, W, (const T*)h->Tt, h->k, h->sm_count, st);
-    else launch_sp_residual<T>(h->csc, (const T*)h->Tt, W, h->k, h->sm_count, st);
-    h->launches++;
+    if (h->sp_refresh_v2) {
+        // the row copy from the factors (16-byte gathers of T' rows), the column copy as a permutation of it
+        launch_sp_residual_rows<T>(h->csr, W, h->k, (const T*)h->Tt, h->sp_ldt, h->k, h->sm_count, st);
+        h->launches++;
+        if (need_csc && h->nnz > 0) {
+            launch_sp_gather<T>(h->sp_perm, (const T*)h->csr.E, (T*)h->csc.E, h->nnz, h->sm_count, st);
+            h->launches++;
+        }
+        return;
+    }
+    if (need_csc) { launch_sp_residual<T>(h->csc, (const T*)h->Tt, W, h->k, h->sm_count, st); h->launches++; }
+    if (need_csr) { launch_sp_residual<T>(h->csr, W, (const T*)h->Tt, h->k, h->sm_count, st); h->launches++; }
 }
 
 template <typename T>
@@ -908,7 +927,7 @@ static int sp_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
         if (allreduce(h, ms, (size_t)2 * d, st)) return 1;
         nu = ms; de = ms + d; parts = 1;
     }
-    launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), trow, 1, (T*)h->Tt + t, h->k, h->flags, st);
+    launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), trow, 1, (T*)h->Tt + t, h->sp_ldt, h->flags, st);
     launch_vec_sum_flag<T>(trow, d, 1, h->sums, t, 1, h->flags, st);
     h->launches += 2;
     S.csc = SpPending{wt, wt, told, trow};       // w_t (told - tnew)'; merged with the W-step's change if one follows
@@ -949,7 +968,7 @@ static int sp_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
 template <typename T>
 static int sp_load_factors(rri_handle_t h, const T* W, const T* Tm, cudaStream_t st)
 {
-    launch_transpose<T>(Tm, h->k, h->d, h->d, (T*)h->Tt, h->k, st);          // T' [d,k]
+    launch_transpose<T>(Tm, h->k, h->d, h->d, (T*)h->Tt, h->sp_ldt, st);     // T' [d,k] (padded row stride)
     launch_transpose<T>(W, h->n, h->k, h->k, (T*)h->Wt, h->ldwt, st);        // W' [k,ldwt]
     h->launches += 2;
     CKL();
@@ -961,8 +980,7 @@ static int sp_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri
 {
     // reference order (nmf.py:415-476); both residual copies restart from the current factors
     SpState S;
-    sp_refresh<T>(h, false, W, st);
-    sp_refresh<T>(h, true, W, st);
+    sp_refresh<T>(h, true, true, W, st);
     for (int t = t0; t < t1; ++t) {
         if (sp_T_step<T>(h, W, Tm, t, p, S, st)) return 1;
         if (sp_W_step<T>(h, W, Tm, t, p, S, st)) return 1;
@@ -983,14 +1001,14 @@ static int sp_sweeps(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_params
         }
         if (!p->fix_T) {                       // block order, T half: only the column copy is read
             SpState S;
-            sp_refresh<T>(h, false, W, st);
+            sp_refresh<T>(h, false, true, W, st);
             for (int t = 0; t < k; ++t) {
                 if (sp_T_step<T>(h, W, Tm, t, p, S, st)) return 1;
                 S.told_cur = nullptr;
             }
         }
         SpState S;                             // W half (also transform(): fix_T): only the row copy is read
-        sp_refresh<T>(h, true, W, st);
+        sp_refresh<T>(h, true, false, W, st);
         for (int t = 0; t < k; ++t)
             if (sp_W_step<T>(h, W, Tm, t, p, S, st)) return 1;
     }
@@ -1131,8 +1149,8 @@ template <typename T>
 static int objective_impl(rri_handle_t h, const T* W, const T* Tm, cudaStream_t st)
 {
     if (h->sparse) {
-        launch_transpose<T>(Tm, h->k, h->d, h->d, (T*)h->Tt, h->k, st);
-        sp_refresh<T>(h, true, W, st);
+        launch_transpose<T>(Tm, h->k, h->d, h->d, (T*)h->Tt, h->sp_ldt, st);
+        sp_refresh<T>(h, true, false, W, st);
         launch_sp_objective<T>(h->csr, h->nnz, h->obj_part, h->obj_out, st);
         launch_norms<T>(W, h->n * h->k, h->obj_part, h->obj_out + 2, st);
         launch_norms<T>(Tm, (int64_t)h->k * h->d, h->obj_part, h->obj_out + 4, st);
@@ -1186,7 +1204,7 @@ static int partials_impl(rri_handle_t h, const T* W, const T* Tm, int t, T* wR, 
     memset(&p, 0, sizeof(p));
     if (h->sparse) {
         if (sp_load_factors<T>(h, W, Tm, st)) return 1;
-        sp_refresh<T>(h, false, W, st);
+        sp_refresh<T>(h, false, true, W, st);
         const T* wt = (const T*)h->Wt + (int64_t)t * h->ldwt;
         launch_sp_pack<T>(nullptr, nullptr, wt, wt, h->sp_quad, h->n, st);
         const int parts = launch_sp_pass<T>(h->csc, h->sp_quad, nullptr, nullptr, Tm + (int64_t)t * d, (T*)h->sp_told,

@@ -182,16 +182,25 @@ void launch_sp_subptr(const int64_t* ptr, const int32_t* idx, int64_t nseg, int 
                       int sm_count, cudaStream_t st);
 
 // Column orientation of a CSR matrix: colptr[d+1], csc_row[nnz], x_csc[nnz] (, w_csc[nnz]); rows ascending inside
-// a column.  Returns 0, a cudaError_t (> 0), or -(bit mask) for a malformed CSR: 1 rowptr, 2 column range,
+// a column; perm[nnz] (caller-owned) receives the CSR position of every CSC entry.  Returns 0, a cudaError_t (> 0), or -(bit mask) for a malformed CSR: 1 rowptr, 2 column range,
 // 4 columns not strictly ascending inside a row.  Synchronises `st`.
 template <typename T>
 int sp_build_csc(const int64_t* rowptr, const int32_t* col, const T* x, const T* w, int64_t n, int64_t d,
-                 int64_t nnz, int64_t* colptr, int32_t* csc_row, T* x_csc, T* w_csc, int sm_count, int* err_dev,
-                 cudaStream_t st);
+                 int64_t nnz, int64_t* colptr, int32_t* csc_row, T* x_csc, T* w_csc, uint32_t* perm, int sm_count,
+                 int* err_dev, cudaStream_t st);
 
 // s.E[p] = s.x[p] - sum_l A[seg,l] * B[s.idx[p],l]   (A: own factor rows [nseg,k], B: other factor rows [.,k])
 template <typename T>
 void launch_sp_residual(const SpSide& s, const T* A, const T* B, int k, int sm_count, cudaStream_t st);
+
+// The same for the row orientation with 16-byte gathers: B[., ldb] has a padded row stride (multiple of 16 bytes, zero
+// pad columns); A[nseg, lda] is staged per segment through shared memory.
+template <typename T>
+void launch_sp_residual_rows(const SpSide& s, const T* A, int64_t lda, const T* B, int ldb, int k, int sm_count,
+                             cudaStream_t st);
+// dst[p] = src[perm[p]]
+template <typename T>
+void launch_sp_gather(const uint32_t* perm, const T* src, T* dst, int64_t nnz, int sm_count, cudaStream_t st);
 
 // quad[i] = {po[i], pn[i], vold[i], vnew[i]}   (po/pn null -> 0): the 16/32-byte gather record of a pass
 template <typename T>

@@ -94,8 +94,8 @@ __global__ void sp_colptr_kernel(const int32_t* __restrict__ keys, int64_t nnz, 
 
 template <typename T>
 int sp_build_csc(const int64_t* rowptr, const int32_t* col, const T* x, const T* w, int64_t n, int64_t d,
-                 int64_t nnz, int64_t* colptr, int32_t* csc_row, T* x_csc, T* w_csc, int sm_count, int* err_dev,
-                 cudaStream_t st)
+                 int64_t nnz, int64_t* colptr, int32_t* csc_row, T* x_csc, T* w_csc, uint32_t* perm, int sm_count,
+                 int* err_dev, cudaStream_t st)
 {
     cudaError_t e;
     const int nb = cap_blocks((nnz + 255) / 256 + (n + 7) / 8, sm_count, 8);
@@ -109,7 +109,7 @@ int sp_build_csc(const int64_t* rowptr, const int32_t* col, const T* x, const T*
         return (int)cudaGetLastError();
     }
     int32_t *rowidx = nullptr, *keys_sorted = nullptr;
-    uint32_t *iota = nullptr, *perm = nullptr;
+    uint32_t* iota = nullptr;
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
     int end_bit = 1;
@@ -119,7 +119,6 @@ int sp_build_csc(const int64_t* rowptr, const int32_t* col, const T* x, const T*
         if ((e = cudaMalloc(&rowidx, sizeof(int32_t) * nnz)) != cudaSuccess) { rc = (int)e; break; }
         if ((e = cudaMalloc(&keys_sorted, sizeof(int32_t) * nnz)) != cudaSuccess) { rc = (int)e; break; }
         if ((e = cudaMalloc(&iota, sizeof(uint32_t) * nnz)) != cudaSuccess) { rc = (int)e; break; }
-        if ((e = cudaMalloc(&perm, sizeof(uint32_t) * nnz)) != cudaSuccess) { rc = (int)e; break; }
         sp_expand_rows_kernel<<<cap_blocks((n + 7) / 8, sm_count, 8), 256, 0, st>>>(rowptr, n, rowidx, iota);
         // stable LSD radix sort of (column, position): rows stay ascending inside every column
         if ((e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, col, keys_sorted, iota, perm, (int)nnz, 0, end_bit,
@@ -133,7 +132,7 @@ int sp_build_csc(const int64_t* rowptr, const int32_t* col, const T* x, const T*
         if ((e = cudaGetLastError()) != cudaSuccess) { rc = (int)e; break; }
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = (int)e; break; }
     } while (0);
-    cudaFree(rowidx); cudaFree(keys_sorted); cudaFree(iota); cudaFree(perm); cudaFree(tmp);
+    cudaFree(rowidx); cudaFree(keys_sorted); cudaFree(iota); cudaFree(tmp);
     return rc;
 }
 
@@ -183,6 +182,80 @@ static void residual_dispatch(const SpSide& s, const T* A, const T* B, int k, in
         sp_residual_kernel<T, V, 32><<<cap_blocks((s.nseg + 7) / 8, sm_count, 8), 256, 0, st>>>(s.ptr, s.idx, (const T*)s.x, A,
                                                                                                  B, k, (T*)s.E, s.nseg);
     }
+}
+
+// Row-orientation residual with the segment's own factor row staged in shared memory and the gathered rows read
+// with 16-byte loads: B has a padded row stride ldb (multiple of 16 bytes, pad columns zero), so an entry costs
+// ceil(k/V) vector loads -- half the L1 tag look-ups of the 8-byte version at k = 50 -- and the own row costs none.
+template <typename T, int G>
+__global__ void __launch_bounds__(256)
+sp_residual_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const T* __restrict__ x,
+                        const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int ldb, int k,
+                        T* __restrict__ E, int64_t nseg)
+{
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    constexpr int GPB = 256 / G;
+    __shared__ __align__(16) T a_s[GPB][256 + VN];
+    const int lane = threadIdx.x % G, g = threadIdx.x / G;
+    const int nv = (k + VN - 1) / VN;
+    for (int64_t s = (int64_t)blockIdx.x * GPB + g; s < nseg; s += (int64_t)gridDim.x * GPB) {
+        if (G == 256) __syncthreads(); else __syncwarp();              // the previous row has been consumed
+        for (int l = lane; l < nv * VN; l += G) a_s[g][l] = l < k ? A[s * lda + l] : T(0);
+        if (G == 256) __syncthreads(); else __syncwarp();
+        const int64_t b = ptr[s], e = ptr[s + 1];
+        const V* __restrict__ av = reinterpret_cast<const V*>(a_s[g]);
+        for (int64_t p = b + lane; p < e; p += G) {
+            const V* __restrict__ bv = reinterpret_cast<const V*>(B + (int64_t)idx[p] * ldb);
+            T acc = x[p];
+#pragma unroll 4
+            for (int l = 0; l < nv; ++l) {
+                T a[VN], c[VN];
+                unpack(av[l], a);
+                unpack(bv[l], c);
+#pragma unroll
+                for (int v = 0; v < VN; ++v) acc = fma(-a[v], c[v], acc);
+            }
+            E[p] = acc;
+        }
+    }
+}
+
+template <typename T>
+void launch_sp_residual_rows(const SpSide& s, const T* A, int64_t lda, const T* B, int ldb, int k, int sm_count,
+                             cudaStream_t st)
+{
+    if (s.group == 256)
+        sp_residual_rows_kernel<T, 256><<<cap_blocks(s.nseg, sm_count, 8), 256, 0, st>>>(s.ptr, s.idx, (const T*)s.x, A, lda, B,
+                                                                                         ldb, k, (T*)s.E, s.nseg);
+    else
+        sp_residual_rows_kernel<T, 32><<<cap_blocks((s.nseg + 7) / 8, sm_count, 8), 256, 0, st>>>(s.ptr, s.idx, (const T*)s.x, A,
+                                                                                                  lda, B, ldb, k, (T*)s.E, s.nseg);
+}
+
+// dst[p] = src[perm[p]]: the column copy of the residual taken from the row copy (bit-identical by construction)
+template <typename T>
+__global__ void sp_gather_kernel(const uint32_t* __restrict__ perm, const T* __restrict__ src, T* __restrict__ dst, int64_t nnz)
+{
+    constexpr int U = 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; p + (U - 1) * stride < nnz; p += U * stride) {
+        uint32_t q[U]; T v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) q[u] = perm[p + u * stride];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = src[q[u]];
+#pragma unroll
+        for (int u = 0; u < U; ++u) dst[p + u * stride] = v[u];
+    }
+    for (; p < nnz; p += stride) dst[p] = src[perm[p]];
+}
+
+template <typename T>
+void launch_sp_gather(const uint32_t* perm, const T* src, T* dst, int64_t nnz, int sm_count, cudaStream_t st)
+{
+    sp_gather_kernel<T><<<cap_blocks((nnz + 1023) / 1024, sm_count, 8), 256, 0, st>>>(perm, src, dst, nnz);
 }
 
 // Staged variant: a warp copies the k-vectors of 32 entries into shared memory with coalesced row reads (two
@@ -244,7 +317,7 @@ static int env_flag(const char* name, int dflt)
 template <typename T>
 void launch_sp_residual(const SpSide& s, const T* A, const T* B, int k, int sm_count, cudaStream_t st)
 {
-    static const int staged = env_flag("RRI_SP_RESID_STAGED", 1);
+    static const int staged = env_flag("RRI_SP_RESID_STAGED", 0);     // measured slower than the direct kernel
     if (staged) {
         const int ld = k | 1;
         const size_t per_warp = (size_t)32 * ld * sizeof(T);
@@ -530,8 +603,10 @@ void launch_sp_objective(const SpSide& s, int64_t nnz, double* part, double* out
 
 #define RRI_INST(T)                                                                                                 \
     template int sp_build_csc<T>(const int64_t*, const int32_t*, const T*, const T*, int64_t, int64_t, int64_t,    \
-                                 int64_t*, int32_t*, T*, T*, int, int*, cudaStream_t);                             \
+                                 int64_t*, int32_t*, T*, T*, uint32_t*, int, int*, cudaStream_t);                  \
     template void launch_sp_residual<T>(const SpSide&, const T*, const T*, int, int, cudaStream_t);                \
+    template void launch_sp_residual_rows<T>(const SpSide&, const T*, int64_t, const T*, int, int, int, cudaStream_t); \
+    template void launch_sp_gather<T>(const uint32_t*, const T*, T*, int64_t, int, cudaStream_t);                  \
     template void launch_sp_pack<T>(const T*, const T*, const T*, const T*, void*, int64_t, cudaStream_t);         \
     template int launch_sp_pass<T>(const SpSide&, const void*, const T*, const T*, const T*, T*, T*, T*, int,      \
                                    cudaStream_t);                                                                  \

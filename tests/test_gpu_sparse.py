@@ -64,7 +64,9 @@ def test_sparse_entry_weights_both_orders(R):
 
 @pytest.mark.parametrize('n,d,density', [(700, 1900, 0.3),     # rows >= 512 entries: a block per row, a warp per column
                                           (1900, 700, 0.3),     # the other way round
-                                          (257, 131, 0.05)])    # short, ragged segments; empty rows and columns
+                                          (257, 131, 0.05),     # short, ragged segments; empty rows and columns
+                                          (9000, 300, 0.05),    # the gathered factor spans several shared-memory blocks
+                                          (300, 9000, 0.05)])   # (4096 records each in fp64), in either orientation
 @pytest.mark.parametrize('order', ['rri', 'hals'])
 def test_sparse_matches_oracle_fp64(R, n, d, density, order):
     k = 8 if n > 500 else 7        # odd k: the residual kernel's scalar path
