@@ -553,23 +553,32 @@ static int bind_csr_impl(rri_handle_t h, const int64_t* rowptr, const int32_t* c
                     (-rc & 2) ? " column index outside [0,d);" : "",
                     (-rc & 4) ? " column indices must be strictly ascending inside every row (sort and merge duplicates);" : "");
     if (rc > 0) return fail("building the column orientation failed: %s", cudaGetErrorString((cudaError_t)rc));
-    h->csr = SpSide{n, rowptr, col, val, wgt, E_csr, nnz / n >= 512 ? 256 : 32, nullptr, 1, 0, d};
+    h->csr = SpSide{n, rowptr, col, val, wgt, E_csr, nnz / n >= 512 ? 256 : 32, nullptr, 1, 0, d, nullptr};
     h->csc = SpSide{d, (const int64_t*)colptr, (const int32_t*)csc_row, x_csc, w_csc, E_csc, nnz / d >= 512 ? 256 : 32,
-                    nullptr, 1, 0, n};
+                    nullptr, 1, 0, n, nullptr};
     h->launches += 8;
     // blocked passes: the gathered factor is staged through shared memory in blocks of nb records
     const char* env = getenv("RRI_SP_BLOCKED");
     const bool blocked = !(env && *env == '0');
-    const int nb = sp_block_len((int)es);
+    const char* env16 = getenv("RRI_SP_IDX16");
+    const bool use16 = !(env16 && *env16 == '0');
     size_t part_elems = (size_t)m;
     for (SpSide* sd : {&h->csr, &h->csc}) {
-        const int64_t nblk = (sd->nother + nb - 1) / nb;
+        int nblk = 1;
+        const int nb = sp_block_len((int)es, sd->nother, &nblk);
         if (!blocked || nblk > 64) continue;          // (a very long factor would make the sub-segments too short)
         void* p2 = nullptr;
+        void* i16 = nullptr;
         if (ws_alloc(h, &p2, sizeof(int64_t) * (size_t)sd->nseg * (size_t)(nblk + 1))) return 1;
+        if (use16 && ws_alloc(h, &i16, sizeof(uint16_t) * ne)) return 1;
         CK(cudaStreamSynchronize(0));
-        launch_sp_subptr(sd->ptr, sd->idx, sd->nseg, (int)nblk, nb, (int64_t*)p2, h->sm_count, st);
-        sd->ptr2 = (const int64_t*)p2; sd->nblk = (int)nblk; sd->nb = nb;
+        launch_sp_subptr(sd->ptr, sd->idx, sd->nseg, nblk, nb, (int64_t*)p2, h->sm_count, st);
+        if (use16 && nnz > 0) {
+            launch_sp_local_index(sd->idx, nnz, nb, (uint16_t*)i16, h->sm_count, st);
+            sd->idx16 = (const uint16_t*)i16;
+            h->launches++;
+        }
+        sd->ptr2 = (const int64_t*)p2; sd->nblk = nblk; sd->nb = nb;
         if ((size_t)nblk * (size_t)sd->nseg > part_elems) part_elems = (size_t)nblk * (size_t)sd->nseg;
         h->launches++;
     }

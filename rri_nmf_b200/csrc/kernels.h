@@ -176,8 +176,10 @@ struct SpSide {            // one compressed orientation of the observed entries
     const int64_t* ptr2;   // [nseg][nblk + 1] first entry of segment s with index >= b * nb, or null
     int nblk, nb;
     int64_t nother;        // length of the other factor's index range (d for CSR, n for CSC)
+    const uint16_t* idx16; // [nnz] idx % nb (2 bytes instead of 4 per entry and pass), or null
 };
-int sp_block_len(int elem_size);
+int sp_block_len(int elem_size, int64_t nother, int* nblk_out);
+void launch_sp_local_index(const int32_t* idx, int64_t nnz, int nb, uint16_t* out, int sm_count, cudaStream_t st);
 void launch_sp_subptr(const int64_t* ptr, const int32_t* idx, int64_t nseg, int nblk, int nb, int64_t* ptr2,
                       int sm_count, cudaStream_t st);
 

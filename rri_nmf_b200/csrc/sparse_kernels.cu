@@ -445,7 +445,8 @@ sp_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
 // numer_part[b][s], denom_part[b][s] and added in block order by the solve kernel (deterministic).
 template <typename T, bool HASW, int U>
 __global__ void __launch_bounds__(1024, 1)
-sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restrict__ idx, T* __restrict__ E,
+sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restrict__ idx,
+                       const uint16_t* __restrict__ idx16, T* __restrict__ E,
                        const T* __restrict__ wgt, const Quad<T>* __restrict__ Q, const T* __restrict__ own_po,
                        const T* __restrict__ own_pn, const T* __restrict__ own_cur, T* __restrict__ own_save,
                        T* __restrict__ numer_part, T* __restrict__ denom_part, int64_t nseg, int nblk, int nb,
@@ -475,7 +476,7 @@ sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restri
             for (int u = 0; u < U; ++u) {
                 const int64_t p = p0 + u * 32;
                 const bool ok = p < end;
-                q[u] = ok ? idx[p] - ibase : -1;
+                q[u] = ok ? (idx16 ? (int32_t)idx16[p] : idx[p] - ibase) : -1;     // block-local record index
                 ev[u] = ok ? E[p] : T(0);
                 m[u] = (HASW && ok) ? wgt[p] : T(1);
             }
@@ -514,7 +515,30 @@ __global__ void sp_subptr_kernel(const int64_t* __restrict__ ptr, const int32_t*
     }
 }
 
-int sp_block_len(int elem_size) { return (128 * 1024) / (4 * elem_size); }      // records per staged block of Q
+// Records per staged block of Q: at most 128 KB of shared memory, and all blocks equally long (a short last block
+// would leave its CTAs with a fraction of the work of the others).
+int sp_block_len(int elem_size, int64_t nother, int* nblk_out)
+{
+    const int64_t cap = (128 * 1024) / (4 * elem_size);
+    const int64_t nblk = nother > 0 ? (nother + cap - 1) / cap : 1;
+    int64_t nb = (nother + nblk - 1) / nblk;
+    nb = (nb + 31) / 32 * 32;
+    if (nb > cap) nb = cap;
+    if (nb < 32) nb = 32;
+    *nblk_out = (int)((nother + nb - 1) / nb > 0 ? (nother + nb - 1) / nb : 1);
+    return (int)nb;
+}
+
+__global__ void sp_local_index_kernel(const int32_t* __restrict__ idx, int64_t nnz, int nb, uint16_t* __restrict__ out)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
+        out[p] = (uint16_t)(idx[p] % nb);
+}
+
+void launch_sp_local_index(const int32_t* idx, int64_t nnz, int nb, uint16_t* out, int sm_count, cudaStream_t st)
+{
+    sp_local_index_kernel<<<cap_blocks((nnz + 255) / 256, sm_count, 8), 256, 0, st>>>(idx, nnz, nb, out);
+}
 
 void launch_sp_subptr(const int64_t* ptr, const int32_t* idx, int64_t nseg, int nblk, int nb, int64_t* ptr2,
                       int sm_count, cudaStream_t st)
@@ -540,7 +564,7 @@ int launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* 
         if (chunks < 1) chunks = 1;
         auto kern = w ? sp_pass_blocked_kernel<T, true, U> : sp_pass_blocked_kernel<T, false, U>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        kern<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx, E, w, Q, own_po, own_pn, own_cur, own_save, numer,
+        kern<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save, numer,
                                                              denom, s.nseg, s.nblk, s.nb, s.nother, chunks);
         return s.nblk;
     }
