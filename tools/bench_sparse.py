@@ -1,6 +1,7 @@
 """Timing of the observed-entries (sparse) WRRI path at config-4 shape, next to the dense masked path on the same
 data:  python tools/bench_sparse.py [rows] [order] [sweeps] [--dense]
-Prints one JSON line per path; bytes/sweep is the algorithmic figure of DESIGN.md (2k passes of 12 B per entry)."""
+Prints one JSON line per path; bytes/sweep is the algorithmic figure of DESIGN.md (2k passes of 10 B per entry:
+2 B block-local index + 4 B residual read + 4 B residual written)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -42,7 +43,7 @@ t0 = time.perf_counter()
 es = R.RRIEngine(Xs, k, order=order)
 torch.cuda.synchronize()
 bind_s = time.perf_counter() - t0
-alg = 2 * k * 12 * nnz          # 2k passes, each: 4 B index + 4 B residual read + 4 B residual written per entry
+alg = 2 * k * 10 * nnz          # 2k passes, each: 2 B index + 4 B residual read + 4 B residual written per entry
 Ws, Ts = timed(es, 'sparse', lambda ms: {'bind_s': round(bind_s, 3), 'algorithmic_GB_per_sweep': round(alg / 1e9, 2),
                                           'achieved_GBps': round(alg / ms / 1e6, 1)})
 es.close()
