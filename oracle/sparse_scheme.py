@@ -52,8 +52,11 @@ class Side(object):
 
 
 class SparseWRRI(object):
-    def __init__(self, rows, cols, vals, n, d, weights=None):
+    def __init__(self, rows, cols, vals, n, d, weights=None, allreduce=None):
+        """allreduce: optional callable summing a vector over the row shards (the multi-GPU exchange of sp_T_step:
+        [numer(d) | denom(d)] of every T-step; W-steps are shard-local)"""
         self.n, self.d = n, d
+        self.allreduce = allreduce
         self.csr = Side(rows, cols, vals, weights, n)
         self.csc = Side(cols, rows, vals, weights, d)
 
@@ -63,6 +66,9 @@ class SparseWRRI(object):
         told = T[t].copy()
         numer, denom = self.csc.half_step(None if pend is None else (pend[0], pend[1]),
                                           None if pend is None else (pend[2], pend[3]), wt, wt, told)
+        if self.allreduce is not None:
+            both = self.allreduce(np.concatenate([numer, denom]))
+            numer, denom = both[:self.d], both[self.d:]
         T[t] = solve_vector_c(numer - reg_l1, denom + reg_l2, EPS, ub)
         S['csc'] = (wt, wt, told, T[t].copy())
         S['told_cur'] = told

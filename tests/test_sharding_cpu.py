@@ -2,7 +2,8 @@
 every rank holds X_i, W_i and a replica of T; per topic the only exchange is an all-reduce of the shard
 statistic [w_t'X_i (d) | w_t'W_i (k)] (reference nmf.py:680-686); the W-step is local.  Here the oracle
 plays the role of the per-rank kernels, so this pins the *host-side* protocol (what is reduced, in what
-order) against the unsharded oracle."""
+order) against the unsharded oracle.  The observed-entries (sparse) path is covered the same way through its
+NumPy scheme model (oracle/sparse_scheme.py): the exchange is [numer(d) | denom(d)] per T-step."""
 import os
 import socket
 
@@ -89,6 +90,57 @@ def test_row_sharded_protocol_world2():
         W, T = out[order]
         assert np.linalg.norm(W - ref['W']) / np.linalg.norm(ref['W']) < 1e-12
         assert np.linalg.norm(T - ref['T']) / np.linalg.norm(ref['T']) < 1e-12
+
+
+def _sparse_worker(rank, world, port, q):
+    """observed-entries path, row-sharded: every rank owns the entries of its rows (both orientations of them);
+    the only exchange is the all-reduce of [numer(d) | denom(d)] in each T-step (api.cu: sp_T_step)"""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from sparse_scheme import SparseWRRI
+    X, W0, T0, M = orc.synth(90, 70, 5, 6, sigma=0.05, seed=6, mask_density=0.3)
+    bounds = np.linspace(0, 90, world + 1).astype(int)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    I, J = M[lo:hi].nonzero()
+
+    def allreduce(v):
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    out = {}
+    for order in ('rri', 'hals'):
+        S = SparseWRRI(I, J, X[lo:hi][I, J], hi - lo, 70, allreduce=allreduce)
+        Wi, T = np.maximum(W0[lo:hi], 0).copy(), np.maximum(T0, 0).copy()
+        S.sweeps(Wi, T, 3, order=order, ub_t=1.0, reg_t_l1=0.01)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (Wi, T))
+        out[order] = gathered
+    if rank == 0:
+        q.put(out)
+    dist.destroy_process_group()
+
+
+def test_row_sharded_sparse_protocol_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sparse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    X, W0, T0, M = orc.synth(90, 70, 5, 6, sigma=0.05, seed=6, mask_density=0.3)
+    for order in ('rri', 'hals'):
+        ref = orc.nmf_oracle(X, 6, W0, T0, max_iter=3, W_mat=M, order=order, t_row_sum=1.0, reg_t_l1=0.01)
+        (Wa, Ta), (Wb, Tb) = out[order]
+        assert np.array_equal(Ta, Tb)                       # replicas of T stay identical
+        W = np.vstack([Wa, Wb])
+        assert np.linalg.norm(W - ref['W']) / np.linalg.norm(ref['W']) < 1e-12
+        assert np.linalg.norm(Ta - ref['T']) / np.linalg.norm(ref['T']) < 1e-12
 
 
 def test_shard_bounds_helper():
