@@ -9,6 +9,10 @@ Additional keyword-only arguments select the device path:
                   'hals' -- block order: all T-steps then all W-steps (2 passes over X per sweep)
     math          'ieee' (default) or 'tf32' (tcgen05 tensor-core contractions; float32 + 'hals')
     comm          engine.NcclComm for a row-sharded multi-GPU run (X, W_in, W_mat are the local shards)
+    init_on_device  where the NNDSVD initialisation runs when W_in/T_in are not both given: True = on the GPU that
+                  holds X (`_device_init.py`; X never returns to the host), False = on the host (`_host.py`, NumPy /
+                  sklearn, as the reference does), None (default) = on the device when X is already a CUDA tensor or
+                  has 2^26 or more elements, on the host otherwise.  Sparse X is always initialised on the host.
 
 X may also be a scipy.sparse matrix or a torch sparse CSR tensor: its STORED entries are the observed ones (the
 recommender setting of sklearn_interface.py:78-102 without densifying the (i, j, rating) triples and without a
@@ -22,6 +26,7 @@ import scipy.sparse as sp
 import torch
 
 from . import _lib
+from ._device_init import initialize_nmf_torch
 from ._host import initialize_nmf, normalize
 from .engine import RRIEngine, EPS_DIV_BY_ZERO
 
@@ -85,6 +90,32 @@ def _sparse_to_device(X, W_mat, device, dtype):
     return RRIEngine.csr_tensor(Xs.indptr, Xs.indices, Xs.data, Xs.shape, device, dtype), wts
 
 
+def _normalize_rows(A):
+    """matrixops.py:124-163 (`normalize`, dim=1, zero_sum_fix) on a device tensor"""
+    s = A.sum(1, keepdim=True) + float(np.spacing(1))
+    out = A / s
+    zero = (s < 1e-10).squeeze(1)
+    if bool(zero.any()):
+        out[zero, :] = 1.0 / A.shape[1]
+    return out
+
+
+def _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum):
+    """nmf.py:840-850 (initialize_nmf on W_mat o X, then the row normalisations) with X staying on its device:
+    initialization.py:80-163 through `_device_init.initialize_nmf_torch`."""
+    Xi = Xd
+    if W_mat is not None:
+        Mi = W_mat if isinstance(W_mat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(W_mat))
+        Xi = Xd * Mi.to(device=Xd.device, dtype=Xd.dtype)
+    Wi, Ti = initialize_nmf_torch(Xi, k, init, random_state=random_state)
+    del Xi
+    if t_row_sum is not None:
+        Ti = _normalize_rows(Ti) * t_row_sum
+    if w_row_sum is not None:
+        Wi = _normalize_rows(Wi) * w_row_sum
+    return Wi.to(Xd.dtype), Ti.to(Xd.dtype)
+
+
 def _to_device(a, device, dtype):
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=dtype)
@@ -104,7 +135,8 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         t_row_sum=None, early_stop=None, reset_topic_method='max_resid_document', fix_reset_seed=False,
         n_resets=23, reg_w_l2=0, reg_t_l2=0, reg_w_l1=0, reg_t_l1=0, diagnostics=[], store_gradients=False,
         ind_rows_to_store=None, eps_gauss_t=None, delta_gauss_t=None,
-        *, device=None, update_order='rri', math='ieee', comm=None, engine=None, sweeps_per_call=16):
+        *, device=None, update_order='rri', math='ieee', comm=None, engine=None, sweeps_per_call=16,
+        init_on_device=None):
     """Non-negative factorisation X ~ W T by rank-one residue iteration.  See the reference docstring
     (nmf.py:109-269) for the arguments; returns {'W', 'T', 'iter_cputime', 'random_state'[, 'obj_history',
     'obj_calculator', 'diagnostics']} (nmf.py:551-560).  W and T come back as the kind of array X was
@@ -171,7 +203,12 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         dtype = torch.float32 if (X.dtype if sparse_in else np.asarray(X).dtype) == np.float32 else torch.float64
 
     # ---- initialisation and validation, as nmf.py:819-880
-    if _is_empty(W_in) or _is_empty(T_in):
+    need_init = _is_empty(W_in) or _is_empty(T_in)
+    if init_on_device is None:
+        init_on_device = (isinstance(X, torch.Tensor) and X.is_cuda) or n * d >= (1 << 26)
+    init_on_device = bool(init_on_device) and need_init and not sparse_in and comm is None
+    W0 = T0 = None
+    if need_init and not init_on_device:
         if sparse_in:
             # M o X is the sparse matrix itself (entry weights folded in): the SVD never densifies it
             if isinstance(X, torch.Tensor):
@@ -211,6 +248,10 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
             Xd, W_mat = _sparse_to_device(X, W_mat, device, dtype)
         else:
             Xd = _to_device(X, device, dtype)
+        if init_on_device:
+            Wi, Ti = _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum)
+            W0 = Wi if W0 is None else W0
+            T0 = Ti if T0 is None else T0
         # np.maximum(W_in, 0) makes copies: the caller's arrays are never mutated (nmf.py:867-868)
         W = _to_device(W0, device, dtype).clamp(min=0).contiguous()
         T = _to_device(T0, device, dtype).clamp(min=0).contiguous()
