@@ -12,7 +12,6 @@
 // rebuilt from X, W, T at the start of every sweep (so N sweeps == N x 1 sweep bit for bit, and rounding drift
 // cannot accumulate).  No atomics: one warp (or one block) owns a whole segment.
 #include <cub/device/device_radix_sort.cuh>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -258,77 +257,12 @@ void launch_sp_gather(const uint32_t* perm, const T* src, T* dst, int64_t nnz, i
     sp_gather_kernel<T><<<cap_blocks((nnz + 1023) / 1024, sm_count, 8), 256, 0, st>>>(perm, src, dst, nnz);
 }
 
-// Staged variant: a warp copies the k-vectors of 32 entries into shared memory with coalesced row reads (two
-// 128-byte lines per entry at k = 50) and every lane then runs the same fma chain as above on its own entry out of
-// shared memory (row stride odd: conflict-free).  The direct kernel pays one L1 tag look-up per lane and k-chunk
-// (32 distinct lines per warp load) and is bound by that; results are bit-identical.
-template <typename T>
-__global__ void __launch_bounds__(256)
-sp_residual_staged_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const T* __restrict__ x,
-                          const T* __restrict__ A, const T* __restrict__ B, int k, T* __restrict__ E, int64_t nseg,
-                          int ld, int wpb)
-{
-    extern __shared__ __align__(16) unsigned char sp_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (warp >= wpb) return;
-    T* __restrict__ tile = reinterpret_cast<T*>(sp_smem) + (size_t)warp * 32 * ld;
-    constexpr int JB = 8;
-    for (int64_t s = (int64_t)blockIdx.x * wpb + warp; s < nseg; s += (int64_t)gridDim.x * wpb) {
-        const int64_t b = ptr[s], e = ptr[s + 1];
-        const T* __restrict__ a = A + s * k;
-        for (int64_t p0 = b; p0 < e; p0 += 32) {
-            const int64_t p = p0 + lane;
-            const bool ok = p < e;
-            const int32_t myidx = ok ? idx[p] : 0;
-            T acc = ok ? x[p] : T(0);
-            const int cnt = (int)((e - p0) < 32 ? (e - p0) : 32);
-            __syncwarp();                                  // the previous tile has been consumed
-            for (int lc = 0; lc < k; lc += 32) {
-                const int l = lc + lane;
-                for (int j0 = 0; j0 < cnt; j0 += JB) {     // loads batched ahead of the shared-memory stores
-                    T v[JB];
-#pragma unroll
-                    for (int u = 0; u < JB; ++u) {
-                        const int64_t r = __shfl_sync(0xffffffffu, myidx, (j0 + u) & 31);
-                        v[u] = (j0 + u < cnt && l < k) ? B[r * k + l] : T(0);
-                    }
-#pragma unroll
-                    for (int u = 0; u < JB; ++u)
-                        if (j0 + u < cnt && l < k) tile[(j0 + u) * ld + l] = v[u];
-                }
-            }
-            __syncwarp();
-            if (ok) {
-                const T* __restrict__ row = tile + lane * ld;
-#pragma unroll 4
-                for (int l = 0; l < k; ++l) acc = fma(-a[l], row[l], acc);
-                E[p] = acc;
-            }
-        }
-    }
-}
-
-static int env_flag(const char* name, int dflt)
-{
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
+// (A variant that staged the gathered k-vectors of 32 entries through shared memory was measured slower than this
+// direct kernel -- 9.5 ms against 5.9 ms at nnz = 1e8, k = 50, profiles/r01_sparse_bench_v2_staged.log -- and was
+// removed; the shipped restart path is sp_residual_rows_kernel + sp_gather_kernel above.)
 template <typename T>
 void launch_sp_residual(const SpSide& s, const T* A, const T* B, int k, int sm_count, cudaStream_t st)
 {
-    static const int staged = env_flag("RRI_SP_RESID_STAGED", 0);     // measured slower than the direct kernel
-    if (staged) {
-        const int ld = k | 1;
-        const size_t per_warp = (size_t)32 * ld * sizeof(T);
-        int wpb = (int)((size_t)48 * 1024 / per_warp);
-        if (wpb > 8) wpb = 8;
-        if (wpb >= 1) {
-            sp_residual_staged_kernel<T><<<cap_blocks((s.nseg + wpb - 1) / wpb, sm_count, 4), wpb * 32, wpb * per_warp, st>>>(
-                s.ptr, s.idx, (const T*)s.x, A, B, k, (T*)s.E, s.nseg, ld, wpb);
-            return;
-        }
-    }
     const uintptr_t al = reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B);
     constexpr int VMAX = 16 / (int)sizeof(T);
     if (VMAX == 4 && k % 4 == 0 && (al & 15) == 0) residual_dispatch<T, VMAX>(s, A, B, k, sm_count, st);
