@@ -43,7 +43,8 @@ typedef struct rri_params_s {
                               vector-c (masked) branch clips, optimization.py:82-83; the scalar
                               branch ignores ub for c>0 (:53-59) and uses it for c<=0 (:63-65) */
     double eps;            /* eps_div_by_zero = np.spacing(10), nmf.py:52, optimization.py:5 */
-    int32_t fix_W, fix_T;  /* nmf.py:417, :460 (fix_W also reproduces the W[:,t]*=nt1 of :450-452) */
+    int32_t fix_W, fix_T;  /* nmf.py:417, :460.  fix_T = W-only sweeps (transform()).  fix_W must be 0: the reference's
+                              T-only sweep also rescales W (:450-452); the host shell drives it from rri_partials_T */
     int32_t simplex_T;     /* project_T_each_iter with s = ub_t: optimization.py:58-59 + nmf.py:759-761 */
     int32_t reserved;
 } rri_params_t;

@@ -62,9 +62,26 @@ def ref_block_sweep(ref, X, W, T, M=None, **regs):
                                              ub=regs.get('w_row_sum'))
 
 
+def make_fix_W(ref):
+    """fix_W=True: T-only sweeps in which, without regularisation, the reference also rescales W[:, t] by the
+    T-step's sum (nmf.py:450-452) -- unmasked / simplex-constrained / regularised / masked."""
+    X, W0, T0, M = orc.synth(120, 80, 5, 6, sigma=0.05, seed=13, mask_density=0.4)
+    d = {}
+    cases = (('plain', {}), ('simplex', dict(project_T_each_iter=True, t_row_sum=1.0)),
+             ('reg', dict(reg_t_l1=0.01, reg_t_l2=0.05)), ('masked', dict(W_mat=M)),
+             ('masked_ub', dict(W_mat=M, t_row_sum=1.0)))
+    for name, kw in cases:
+        r = ref_nmf(ref, X, 6, W0, T0, max_iter=3, fix_W=True, **kw)
+        d['W_' + name], d['T_' + name] = r['W'], r['T']
+    np.savez_compressed(os.path.join(OUT, 'fixW_f64.npz'), **d)
+
+
 def main():
     ref = refshim.load()
     os.makedirs(OUT, exist_ok=True)
+    make_fix_W(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == 'fixW':
+        return
 
     # ---------------------------------------------------------------- cfg1: 500x300 k=10 fp64
     X, W0, T0 = orc.synth(500, 300, 10, 10, sigma=0.0, seed=0)

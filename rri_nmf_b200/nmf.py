@@ -170,8 +170,13 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
     if store_gradients:
         raise NotImplementedError('store_gradients: use RRIEngine.partials_T (the statistic of nmf.py:680-686)')
     if fix_W:
-        raise NotImplementedError('fix_W=True is not on the device path (the reference T-only sweep also '
-                                  'rescales W, nmf.py:450-452)')
+        # T-only sweeps: per topic the statistic comes from the engine (rri_partials_T, nmf.py:680-686 / :706-713),
+        # the solve and the reference's W[:, t] *= nt1 rescaling (nmf.py:450-452) are a few device vector ops
+        update_order = 'rri'
+        if math != 'ieee':
+            raise ValueError("fix_W=True runs with math='ieee'")
+        if comm is not None:
+            raise NotImplementedError('fix_W=True is not available on row shards')
     if w_row_sum is not None and not np.isscalar(w_row_sum):
         raise NotImplementedError('vector w_row_sum is not on the device path')
     if type(diagnostics) is not list:
@@ -357,7 +362,11 @@ def _solve(engine, Xd, W, T, rtv, a):
         ns = min(chunk, max_iter - iter_no)
         if can_reset:
             W_save, T_save = W.clone(), T.clone()
-        flags = engine.sweeps(W, T, ns, params, want_flags=True)
+        if a['fix_W']:
+            ns = 1
+            flags = 0 if fix_T else _sweep_fix_W(engine, W, T, a)
+        else:
+            flags = engine.sweeps(W, T, ns, params, want_flags=True)
         if flags & (_lib.FLAG_ZERO_T | _lib.FLAG_ZERO_W) and can_reset and state['n_resets_remaining'] > 0:
             # rare path: redo this sweep topic by topic with the reset policy of nmf.py:762-783, :796-816
             W.copy_(W_save)
@@ -391,6 +400,65 @@ def _solve(engine, Xd, W, T, rtv, a):
     rtv['iter_cputime'] = iter_cputime
     rtv['random_state'] = a['random_state']
     return rtv
+
+
+def _qf_min_device(numer, denom, s, ub, engine):
+    """qf_min(-numer, denom, s=s, ub=ub) of optimization.py:12-88 on device vectors: returns (x, nx) with
+    nx = sum(x) before the projection / rescaling to sum s.  denom with one element = the scalar-c branches
+    (:51-74), otherwise the vector-c branch (:75-87)."""
+    d = numer.numel()
+    eps = eps_div_by_zero
+    if s:                                                         # :43-49
+        if ub:
+            ub = min(ub, s)
+            assert d * ub >= s
+        else:
+            ub = s
+    if denom.numel() == 1:
+        c = float(denom)
+        if c > 0:                                                 # :53-59 (ub is ignored on this branch)
+            x = numer.clamp(min=0) / (c + eps)
+            nx = float(x.sum())
+            if s is not None:
+                x = engine.project_rows_simplex(x.reshape(1, -1).contiguous(), s).reshape(-1)
+            return x, nx
+        x = torch.zeros_like(numer)                               # :60-74
+        if s is None:
+            if not ub:
+                raise ValueError('Minimum objective is unbounded.')
+            x[(c - numer) < 0] = ub
+        elif s == 1.0:
+            x[int(torch.argmax(numer))] = 1.0
+        else:
+            raise NotImplementedError('s={} is not yet implemented'.format(s))
+        return x, 1.0
+    if bool((denom < 0).any()) and (s is None and ub is None):    # :76-77
+        raise ValueError('Minimum objective is unbounded.')
+    x = torch.where(denom > 0, numer.clamp(min=0) / (denom + eps), torch.zeros_like(numer))
+    if ub is not None:
+        x = x.clamp(max=ub)
+    nx = float(x.sum())
+    if s is not None:
+        x = s * x / x.sum()
+    return x, nx
+
+
+def _sweep_fix_W(engine, W, T, a):
+    """One T-only sweep in the reference's order (nmf.py:415-458 with fix_W=True): for every topic the shard
+    statistic of rri_partials_T, the qf_min solve, and -- when no regulariser is set -- the rescaling
+    W[:, t] *= nt1 of nmf.py:450-452 that keeps W T invariant under the row normalisation of T."""
+    t_row_sum = a['t_row_sum']
+    s = t_row_sum if a['project_T_each_iter'] else None           # nmf.py:442-445
+    noreg = (abs(a['reg_w_l1']) + abs(a['reg_w_l2']) + abs(a['reg_t_l1']) + abs(a['reg_t_l2'])) == 0
+    for t in range(a['k']):
+        wR, nw = engine.partials_T(W, T, t)
+        x, nt1 = _qf_min_device(wR - a['reg_t_l1'], nw + a['reg_t_l2'], s, t_row_sum, engine)
+        T[t, :] = x
+        if noreg:
+            W[:, t] *= nt1
+        if t_row_sum and a['project_T_each_iter'] and abs(float(T[t, :].sum()) - t_row_sum) > 1e-15:
+            engine.project_rows_simplex(T[t:t + 1, :], t_row_sum)               # nmf.py:759-761
+    return 0
 
 
 def _raise_on_flags(flags, engine):

@@ -26,3 +26,25 @@ def test_device_init_equals_host_init(cuda_device):
     a = R.nmf(X, 8, W_mat=M, init_on_device=False, **kw)
     b = R.nmf(X, 8, W_mat=M, init_on_device=True, **kw)
     assert relfro(b['W'], a['W']) < 1e-6 and relfro(b['T'], a['T']) < 1e-6
+
+
+@pytest.mark.parametrize('name,kw', [('plain', {}), ('simplex', dict(project_T_each_iter=True, t_row_sum=1.0)),
+                                      ('reg', dict(reg_t_l1=0.01, reg_t_l2=0.05)), ('masked', dict(masked=True)),
+                                      ('masked_ub', dict(masked=True, t_row_sum=1.0))])
+def test_fix_W_matches_reference(cuda_device, name, kw):
+    """fix_W=True: T-only sweeps + the W[:, t] *= nt1 rescaling of nmf.py:450-452, against the unmodified reference
+    (tests/golden/fixW_f64.npz); statistic from rri_partials_T, solve on device vectors"""
+    import scipy.sparse as sp
+    import rri_nmf_b200 as R
+    from conftest import golden
+    X, W0, T0, M = orc.synth(120, 80, 5, 6, sigma=0.05, seed=13, mask_density=0.4)
+    kw = dict(kw)
+    masked = kw.pop('masked', False)
+    g = golden('fixW_f64.npz')
+    common = dict(W_in=W0, T_in=T0, max_iter=3, fix_W=True, reset_topic_method=None, eps_stop=-1.0, max_time=1e9)
+    out = R.nmf(X, 6, W_mat=M if masked else None, **common, **kw)
+    assert relfro(out['W'], g['W_' + name]) < 1e-9 and relfro(out['T'], g['T_' + name]) < 1e-9
+    if masked:
+        I, J = M.nonzero()
+        out = R.nmf(sp.csr_matrix((X[I, J], (I, J)), shape=X.shape), 6, **common, **kw)
+        assert relfro(out['W'], g['W_' + name]) < 1e-9 and relfro(out['T'], g['T_' + name]) < 1e-9
