@@ -1,10 +1,9 @@
-"""GPU tests of the two features that were finished after the GPU budget of round 1 was spent, so their first
-execution is the driver's round-end run (the file sorts last on purpose: with `-x` nothing else is held up):
+"""GPU tests of the device-resident initialisation and of fix_W=True:
 
 * device-resident NNDSVD initialisation -- same fit as with the host initialisation; the
-  torch code itself is checked against the host implementation on CPU (tests/test_device_init_cpu.py);
+  torch code itself is also checked against the host implementation on CPU (tests/test_device_init_cpu.py);
 * fix_W=True (T-only sweeps with the W[:, t] *= nt1 rescaling of nmf.py:450-452) against the unmodified reference;
-  the host-side sweep is checked on CPU with the engine calls served by the oracle (tests/test_fixw_cpu.py)."""
+  the host-side sweep is also checked on CPU with the engine calls served by the oracle (tests/test_fixw_cpu.py)."""
 import numpy as np
 import pytest
 import torch
