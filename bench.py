@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--rows', type=int, default=None, help='override n (debugging; the line then says so)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-pageable', action='store_true', help='skip the e2e run from pageable host arrays')
     ap.add_argument('--no-rri', action='store_true', help='skip the side measurement of the reference-exact order')
     ap.add_argument('--cpu-rows', type=int, default=None)
     return ap.parse_args()
@@ -121,62 +122,112 @@ class ClockSampler(object):
                 'power_w_max': max(pw) if pw else None, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def gen_shard(torch, cfg, rows, row0, device, seed):
-    """X = U V + sigma*mean(UV)*E, uniform factors, generated on the device in row
-    chunks; the shard's rows are rows [row0, row0+rows) of the global matrix in distribution only."""
+GEN_BLOCK = 8192
+
+
+def gen_shard(torch, cfg, rows, row0, device, seed=None):
+    """Rows [row0, row0+rows) of the GLOBAL matrix X = U V + sigma*mean(UV)*E (uniform factors),
+    generated on the device.  Every block of GEN_BLOCK global rows has its own generator seed, so the matrix (and
+    W0) do not depend on how the rows are sharded: N = 1, 2, 4, 8 ranks factorise the SAME matrix and the line's
+    `final_rel_error` must agree across N.  (`seed` is accepted for older callers and ignored.)"""
     d, r = cfg['d'], cfg['k']
     dt = torch.float32 if cfg['dtype'] == 'f32' else torch.float64
     g = torch.Generator(device=device)
     g.manual_seed(4242)
     V = torch.rand(r, d, generator=g, device=device, dtype=dt)          # shared by all shards
-    g.manual_seed(1000 + seed)
     X = torch.empty(rows, d, device=device, dtype=dt)
+    W0 = torch.empty(rows, cfg['k'], device=device, dtype=dt)
     mean_uv = 0.25 * r                                                    # E[u v] * r for U[0,1) factors
-    step = 8192
-    for b in range(0, rows, step):
-        e = min(rows, b + step)
-        U = torch.rand(e - b, r, generator=g, device=device, dtype=dt)
-        torch.matmul(U, V, out=X[b:e])
+    Xb = torch.empty(GEN_BLOCK, d, device=device, dtype=dt)
+    for gb in range(row0 // GEN_BLOCK, (row0 + rows + GEN_BLOCK - 1) // GEN_BLOCK):
+        # the whole block is generated with block-independent shapes (same cuBLAS kernel, same Philox stream on
+        # every rank) and the shard's slice of it is kept
+        g.manual_seed(100000 + gb)
+        U = torch.rand(GEN_BLOCK, r, generator=g, device=device, dtype=dt)
+        torch.matmul(U, V, out=Xb)
         if cfg['sigma']:
-            X[b:e].add_(torch.rand(e - b, d, generator=g, device=device, dtype=dt), alpha=cfg['sigma'] * mean_uv)
-    W0 = torch.rand(rows, cfg['k'], generator=g, device=device, dtype=dt)
+            Xb.add_(torch.rand(GEN_BLOCK, d, generator=g, device=device, dtype=dt), alpha=cfg['sigma'] * mean_uv)
+        Wb = torch.rand(GEN_BLOCK, cfg['k'], generator=g, device=device, dtype=dt)
+        lo, hi = max(row0, gb * GEN_BLOCK), min(row0 + rows, (gb + 1) * GEN_BLOCK)
+        X[lo - row0:hi - row0] = Xb[lo - gb * GEN_BLOCK:hi - gb * GEN_BLOCK]
+        W0[lo - row0:hi - row0] = Wb[lo - gb * GEN_BLOCK:hi - gb * GEN_BLOCK]
+    del Xb
     g.manual_seed(77)
     T0 = torch.rand(cfg['k'], d, generator=g, device=device, dtype=dt)   # replicated
     return X, W0, T0
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sweeps(cfg, rows, sweeps, warm=1):
-    """Time the oracle port of the reference's sweep (per-topic GEMVs over X, nmf.py:415-476, interleaved
-    order) on the host cores, on a row sample of the configuration; cost is exactly linear in n, so the
-    full-size figure is the sample's rate scaled by rows/n."""
-    import numpy as np
+REF_COPY = os.path.join(ROOT, 'oracle', '_ref')      # build-time copy of the reference's sources (git-ignored)
+
+
+def _load_cpu_arm():
+    """(kind, sweep_runner): the UNMODIFIED reference `nmf()` through oracle/refshim.py when `build()` left a copy of
+    its sources under oracle/_ref/ (kind 'reference'), else the NumPy restatement oracle/rri_oracle.py ('port')."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import rri_oracle as orc
-    try:
-        from threadpoolctl import threadpool_info
-        info = [i for i in threadpool_info() if i.get('user_api') == 'blas']
-        blas = '%s %s, %d threads' % (info[0].get('internal_api'), info[0].get('version'), info[0].get('num_threads')) if info else 'unknown BLAS'
-        threads = info[0].get('num_threads') if info else len(os.sched_getaffinity(0))
-    except Exception:
-        blas, threads = 'unknown BLAS', len(os.sched_getaffinity(0))
+    if os.path.isfile(os.path.join(REF_COPY, 'src', 'rri_nmf', 'nmf.py')) and not os.environ.get('RRI_BENCH_PORT'):
+        try:
+            os.environ['RRI_REFERENCE_ROOT'] = REF_COPY
+            import refshim
+            refshim.REF_ROOT = REF_COPY
+            ref = refshim.load()
+
+            def run(X, k, W, T, sweeps):
+                r = ref.nmf.nmf(X, k, W_in=W, T_in=T, max_iter=sweeps, max_time=1e9, eps_stop=-1.0,
+                                compute_obj_each_iter=False, reset_topic_method=None)
+                return r['W'], r['T']
+            return 'reference', run, orc
+        except Exception as ex:                    # a broken copy must not take the bench line down
+            sys.stderr.write('reference copy under oracle/_ref unusable (%r); timing the port\n' % (ex,))
+
+    def run(X, k, W, T, sweeps):
+        W, T = W.copy(), T.copy()
+        for _ in range(sweeps):
+            orc.sweep(X, W, T, order='rri')
+        return W, T
+    return 'port', run, orc
+
+
+def cpu_reference_sweeps(cfg, rows, sweeps, warm=1):
+    """Time the reference's sweep (per-topic GEMVs over X, nmf.py:415-476, interleaved order -- the only order it
+    has) on ALL host cores, on a row sample of the configuration; its cost is exactly linear in n, so the
+    full-size figure is the sample's rate scaled by rows/n.  BLAS threads are forced to the number of available
+    cores whatever OMP_NUM_THREADS says (torch.distributed.run exports OMP_NUM_THREADS=1)."""
+    import numpy as np
+    from threadpoolctl import threadpool_info, threadpool_limits
+    ncores = len(os.sched_getaffinity(0))
+    kind, run, orc = _load_cpu_arm()
     dt = np.float32 if cfg['dtype'] == 'f32' else np.float64
     X, W0, T0 = orc.synth(rows, cfg['d'], cfg['k'], cfg['k'], sigma=cfg['sigma'], seed=0, dtype=dt)
     W, T = np.maximum(W0, 0), np.maximum(T0, 0)
-    for _ in range(warm):
-        orc.sweep(X, W, T, order='rri')
-    t0 = time.perf_counter()
-    for _ in range(sweeps):
-        orc.sweep(X, W, T, order='rri')
-    dtm = (time.perf_counter() - t0) / sweeps
+    with threadpool_limits(limits=ncores, user_api='blas'):
+        info = [i for i in threadpool_info() if i.get('user_api') == 'blas']
+        blas = '%s %s' % (info[0].get('internal_api'), info[0].get('version')) if info else 'unknown BLAS'
+        threads = int(info[0].get('num_threads')) if info else ncores
+        if warm > 0:
+            W, T = run(X, cfg['k'], W, T, warm)
+        t0 = time.perf_counter()
+        W, T = run(X, cfg['k'], W, T, sweeps)
+        dtm = (time.perf_counter() - t0) / sweeps
     full = dtm * cfg['n'] / rows
-    return {'value': 1.0 / full, 'unit': 'sweeps/s', 'cores': int(threads), 'kind': 'port',
-            'sample': '%d of %d rows (all %d columns, k=%d, %s), %d sweeps of the interleaved reference order '
-                      '(2k GEMV passes, nmf.py:415-476) timed after %d warm-up, %.3f s/sweep on the sample, scaled '
-                      'linearly in n; %s; host cores available %d'
-                      % (rows, cfg['n'], cfg['d'], cfg['k'], cfg['dtype'], sweeps, warm, dtm, blas,
-                         len(os.sched_getaffinity(0))),
-            'ms_per_sweep_sample': dtm * 1e3}
+    what = ('the UNMODIFIED reference nmf() (oracle/_ref copy of src/rri_nmf, py3 shim, logger at WARNING)'
+            if kind == 'reference' else 'the NumPy port oracle/rri_oracle.py of the reference sweep')
+    return {'value': 1.0 / full, 'unit': 'sweeps/s', 'cores': threads, 'kind': kind,
+            'sample': '%s on %d of %d rows (all %d columns, k=%d, %s): %d sweeps of the interleaved reference order '
+                      '(2k GEMV passes over X, nmf.py:415-476) timed after %d warm-up, %.3f s/sweep on the sample, scaled '
+                      'linearly in n; %s with %d BLAS threads (forced with threadpoolctl); host cores available %d'
+                      % (what, rows, cfg['n'], cfg['d'], cfg['k'], cfg['dtype'], sweeps, warm, dtm, blas, threads, ncores),
+            'ms_per_sweep_sample': dtm * 1e3, 'sample_rows': rows, 'blas_threads': threads,
+            'host_cores': ncores}
+
+
+def cpu_sample_rows(cfg, sweeps, seconds):
+    """rows of the sample so that `sweeps` reference sweeps take about `seconds` of wall time (the reference moves
+    2k x rows x d elements per sweep at roughly 40 GB/s on these hosts)"""
+    es = 4 if cfg['dtype'] == 'f32' else 8
+    per_row = 2.0 * cfg['k'] * cfg['d'] * es / 40e9
+    return int(min(cfg['n'], max(256, seconds / (max(1, sweeps) * per_row))))
 
 
 def main_reference(args):
@@ -186,19 +237,18 @@ def main_reference(args):
     cfg = dict(CONFIGS[args.config])
     if args.rows:
         cfg['n'] = args.rows
-    # bounded sample: n/40 rows, fewer when K is large, so that K timed sweeps stay around a minute of CPU time
-    # (the port moves 2k x rows x d elements per sweep at roughly 40 GB/s on these hosts)
     steps = max(1, args.steps)
-    es = 4 if cfg['dtype'] == 'f32' else 8
-    per_row = 2.0 * cfg['k'] * cfg['d'] * es / 40e9
-    rows = args.cpu_rows or int(min(cfg['n'], max(256, min(cfg['n'] // 40, 60.0 / (steps * per_row)))))
+    # bounded sample: K timed sweeps (+ warm-up) stay around a minute of CPU time
+    rows = args.cpu_rows or cpu_sample_rows(cfg, steps + min(args.warmup, 1), 60.0)
     cb = cpu_reference_sweeps(cfg, rows, sweeps=steps, warm=max(0, min(args.warmup, 1)))
     line = {
         'impl': 'reference', 'metric': 'RRI sweeps/sec', 'value': cb['value'], 'unit': 'sweeps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': cfg['dtype'], 'data': 'synthetic',
         'config': {'workload': '%s: dense %dx%d low-rank-plus-noise, k=%d, %s' % (args.config, cfg['n'], cfg['d'], cfg['k'], cfg['dtype']),
-                   'update_order': 'rri (the reference has only the interleaved order)', 'sample_rows': rows},
+                   'update_order': 'rri (the reference has only the interleaved order; the GPU arm reports the same '
+                                   'order under "reference_order" and the ratio under "like_for_like")',
+                   'sample_rows': rows},
         'cpu_baseline': cb,
         'e2e': {'value': cb['value'], 'unit': 'sweeps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
@@ -239,7 +289,7 @@ def main_ours(args):
     n, d, k = cfg['n'], cfg['d'], cfg['k']
     es = 4 if cfg['dtype'] == 'f32' else 8
     b, e = shard_bounds(n, world)[rank]
-    X, W0, T0 = gen_shard(torch, cfg, e - b, b, device, seed=rank)
+    X, W0, T0 = gen_shard(torch, cfg, e - b, b, device)
     eng = R.RRIEngine(X, k, order=args.order, math=math, comm=comm)
     params = eng.params()
     peer_x = bool(getattr(eng, 'peer_exchange', False))
@@ -298,7 +348,9 @@ def main_ours(args):
                 'sweep_effective_gbs': passes * alg_bytes / (ms_per_step * 1e-3) / 1e9,
                 'kernel_share_of_step': passes * kms / ms_per_step}
 
-    # ---- e2e: the public call with HOST buffers (pinned), copies inside the timed region
+    # ---- e2e: the public call with HOST buffers, copies inside the timed region.  Two figures: pinned host arrays
+    # (the headline e2e) and plain pageable NumPy arrays (what a drop-in user passes; nmf() stages them through
+    # its own pinned chunk buffers)
     e2e = None
     if not args.no_e2e:
         try:
@@ -306,27 +358,43 @@ def main_ours(args):
             Xh.copy_(X)
             Wh, Th = W0.cpu().pin_memory(), T0.cpu().pin_memory()
             eng.close()
+            del eng
             torch.cuda.synchronize()
             s_e2e = args.steps
-            barrier()
-            t0 = time.perf_counter()
-            out = R.nmf(Xh.numpy(), k, W_in=Wh.numpy(), T_in=Th.numpy(), max_iter=s_e2e, reset_topic_method=None,
-                        max_time=1e9, update_order=args.order, math=math, device=device, comm=comm)
-            _ = float(out['W'][0, 0])
-            t_call = time.perf_counter() - t0
-            barrier()
-            dt = time.perf_counter() - t0
-            if world > 1:
-                tt = torch.tensor([dt], device=device, dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                dt = float(tt.item())
+
+            def e2e_call(Xa, Wa, Ta):
+                barrier()
+                t0 = time.perf_counter()
+                out = R.nmf(Xa, k, W_in=Wa, T_in=Ta, max_iter=s_e2e, reset_topic_method=None,
+                            max_time=1e9, update_order=args.order, math=math, device=device, comm=comm)
+                _ = float(out['W'][0, 0])
+                t_call = time.perf_counter() - t0
+                barrier()
+                dt = time.perf_counter() - t0
+                if world > 1:
+                    tt = torch.tensor([dt], device=device, dtype=torch.float64)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    dt = float(tt.item())
+                return dt, dict(out.get('timing', {}), call_s=t_call)
+
+            e2e_call(Xh.numpy()[:1024], Wh.numpy()[:1024], Th.numpy())          # library/allocator warm-up, untimed
+            dt, ph = e2e_call(Xh.numpy(), Wh.numpy(), Th.numpy())
             hb = (Xh.numel() + Wh.numel() + Th.numel()) * es * world
             db = (Wh.numel() + Th.numel()) * es * world
             e2e = {'value': s_e2e / dt, 'unit': 'sweeps/s', 'h2d_bytes_per_step': hb / s_e2e,
                    'd2h_bytes_per_step': db / s_e2e,
                    'what': 'rri_nmf_b200.nmf(X_host, k, W_in, T_in, max_iter=%d) from pinned host arrays: H2D of X/W/T, '
                            '%d sweeps, D2H of W/T; %.3f s total' % (s_e2e, s_e2e, dt),
-                   'rank0_phases_s': dict(out.get('timing', {}), call_s=t_call)}
+                   'rank0_phases_s': ph}
+            if not args.no_pageable:
+                Xp = np.empty(tuple(X.shape), dtype=np.float32 if es == 4 else np.float64)   # pageable
+                Xp[...] = Xh.numpy()
+                Wp, Tp = np.array(Wh.numpy()), np.array(Th.numpy())
+                del Xh
+                dtp, php = e2e_call(Xp, Wp, Tp)
+                e2e['pageable'] = {'value': s_e2e / dtp, 'unit': 'sweeps/s', 'total_s': dtp, 'rank0_phases_s': php,
+                                   'what': 'the same call with plain (pageable) NumPy arrays', 'vs_pinned': dtp / dt}
+                del Xp
         except Exception as ex:        # host RAM too small for a pinned copy, etc.
             e2e = {'value': None, 'unit': 'sweeps/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None,
                    'error': repr(ex)[:200]}
@@ -361,8 +429,8 @@ def main_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rows = args.cpu_rows or min(n, max(256, n // 40))
-        cpu = cpu_reference_sweeps(cfg, rows, sweeps=2, warm=1)
+        rows = args.cpu_rows or cpu_sample_rows(cfg, 6, 20.0)      # 5 timed sweeps + 1 warm-up in about 20 s
+        cpu = cpu_reference_sweeps(cfg, rows, sweeps=5, warm=1)
 
     if rank == 0:
         line = {
@@ -378,6 +446,15 @@ def main_ours(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'reference_order': rri_side,
         }
+        if cpu and rri_side and rri_side.get('value'):
+            # same update order on both sides: the reference's interleaved sweep on the GPU over the CPU figure
+            line['like_for_like'] = {'update_order': 'rri (nmf.py:415-476) on both sides', 'gpu_value': rri_side['value'],
+                                     'cpu_value': cpu['value'], 'ratio': rri_side['value'] / cpu['value'],
+                                     'cpu_kind': cpu['kind'], 'cpu_cores': cpu['cores']}
+        elif cpu and args.order == 'rri':
+            line['like_for_like'] = {'update_order': 'rri (nmf.py:415-476) on both sides', 'gpu_value': value,
+                                     'cpu_value': cpu['value'], 'ratio': value / cpu['value'],
+                                     'cpu_kind': cpu['kind'], 'cpu_cores': cpu['cores']}
         print(json.dumps(line))
     if world > 1:
         if comm is not None:

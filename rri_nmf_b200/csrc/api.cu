@@ -151,6 +151,7 @@ struct rri_handle_s {
     uint32_t* sp_perm = nullptr;       // [nnz] CSR position of every CSC entry
     int sp_ldt = 0;                    // row stride of T' [d, sp_ldt] (k rounded up to 16 bytes: vector gathers)
     bool sp_refresh_v2 = true;         // residual restart: row copy from the factors, column copy gathered from it
+    bool sp_batched_sums = false;      // candidate: per-topic sums once per sweep instead of once per half-step
     int* sp_err = nullptr;
     // common
     double* sums = nullptr;    // [2k] device
@@ -526,7 +527,8 @@ static int bind_csr_impl(rri_handle_t h, const int64_t* rowptr, const int32_t* c
     const size_t ne = (size_t)(nnz > 0 ? nnz : 1);
     void *E_csr = nullptr, *E_csc = nullptr, *x_csc = nullptr, *w_csc = nullptr, *csc_row = nullptr, *colptr = nullptr;
     if (ws_alloc(h, (void**)&h->obj_part, sizeof(double) * 2 * 256) || ws_alloc(h, (void**)&h->obj_out, sizeof(double) * 8)) return 1;
-    if (ws_alloc(h, &E_csr, es * ne) || ws_alloc(h, &E_csc, es * ne) || ws_alloc(h, &x_csc, es * ne)) return 1;
+    // (+2 elements: the paired loads of the candidate pass kernel may touch one entry past a segment's end)
+    if (ws_alloc(h, &E_csr, es * (ne + 2)) || ws_alloc(h, &E_csc, es * (ne + 2)) || ws_alloc(h, &x_csc, es * ne)) return 1;
     if (wgt && ws_alloc(h, &w_csc, es * ne)) return 1;
     if (ws_alloc(h, &csc_row, sizeof(int32_t) * ne) || ws_alloc(h, &colptr, sizeof(int64_t) * (size_t)(d + 1))) return 1;
     if (ws_alloc(h, &h->sp_quad, 4 * es * (size_t)m) || ws_alloc(h, &h->sp_told, es * 2 * (size_t)d) ||
@@ -540,6 +542,8 @@ static int bind_csr_impl(rri_handle_t h, const int64_t* rowptr, const int32_t* c
     {
         const char* env = getenv("RRI_SP_REFRESH_V2");
         h->sp_refresh_v2 = !(env && *env == '0');
+        const char* envb = getenv("RRI_SP_BATCHED_SUMS");
+        h->sp_batched_sums = envb && *envb == '1';
         const int v = 16 / (int)es;
         h->sp_ldt = h->sp_refresh_v2 ? (k + v - 1) / v * v : k;
     }
@@ -570,7 +574,7 @@ static int bind_csr_impl(rri_handle_t h, const int64_t* rowptr, const int32_t* c
         void* p2 = nullptr;
         void* i16 = nullptr;
         if (ws_alloc(h, &p2, sizeof(int64_t) * (size_t)sd->nseg * (size_t)(nblk + 1))) return 1;
-        if (use16 && ws_alloc(h, &i16, sizeof(uint16_t) * ne)) return 1;
+        if (use16 && ws_alloc(h, &i16, sizeof(uint16_t) * (ne + 2))) return 1;
         CK(cudaStreamSynchronize(0));
         launch_sp_subptr(sd->ptr, sd->idx, sd->nseg, nblk, nb, (int64_t*)p2, h->sm_count, st);
         if (use16 && nnz > 0) {
@@ -937,8 +941,8 @@ static int sp_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
         nu = ms; de = ms + d; parts = 1;
     }
     launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), trow, 1, (T*)h->Tt + t, h->sp_ldt, h->flags, st);
-    launch_vec_sum_flag<T>(trow, d, 1, h->sums, t, 1, h->flags, st);
-    h->launches += 2;
+    h->launches++;
+    if (!h->sp_batched_sums) { launch_vec_sum_flag<T>(trow, d, 1, h->sums, t, 1, h->flags, st); h->launches++; }
     S.csc = SpPending{wt, wt, told, trow};       // w_t (told - tnew)'; merged with the W-step's change if one follows
     S.told_cur = told;
     S.ct++;
@@ -958,12 +962,15 @@ static int sp_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
                                         (T*)h->sp_npart, (T*)h->sp_dpart, h->sm_count, st);
     launch_wrri_final<T>((const T*)h->sp_npart, (const T*)h->sp_dpart, parts, n, solve_args(p, false), W + t, h->k, wt, 1,
                          h->flags, st);
-    launch_vec_sum_flag<T>(wt, n, 1, h->sums, h->k + t, h->world > 1 ? 0 : 2, h->flags, st);
-    h->launches += 4;
-    if (h->world > 1) {
-        NCK(g_nccl.AllReduce(h->sums + h->k + t, h->sums + h->k + t, 1, 8, 0, h->comm, st));
-        launch_flag_from_sums(h->sums, h->k + t, 1, 2, h->flags, st);
-        h->launches += 2;
+    h->launches += 3;
+    if (!h->sp_batched_sums) {
+        launch_vec_sum_flag<T>(wt, n, 1, h->sums, h->k + t, h->world > 1 ? 0 : 2, h->flags, st);
+        h->launches++;
+        if (h->world > 1) {
+            NCK(g_nccl.AllReduce(h->sums + h->k + t, h->sums + h->k + t, 1, 8, 0, h->comm, st));
+            launch_flag_from_sums(h->sums, h->k + t, 1, 2, h->flags, st);
+            h->launches += 2;
+        }
     }
     // both copies now lag by  wold told' - wnew tnew'  (one record even when a T-step preceded: the terms in
     // w_old t_new' cancel)
@@ -971,6 +978,26 @@ static int sp_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
     if (S.told_cur) S.csc = S.csr;
     S.told_cur = nullptr;
     S.cw++;
+    return 0;
+}
+
+// CANDIDATE (RRI_SP_BATCHED_SUMS=1, unmeasured): the 2k single-block column-sum launches of a sweep (13.6 us each at
+// config-4 shape) replaced by two launches at its end -- row t of T and of W' is final once its step has run.
+template <typename T>
+static int sp_topic_sums(rri_handle_t h, const T* Tm, int t0, int t1, bool did_T, bool did_W, cudaStream_t st)
+{
+    if (!h->sp_batched_sums) return 0;
+    if (did_T) { launch_rowsum_flag<T>(Tm + (int64_t)t0 * h->d, t1 - t0, h->d, h->d, h->sums, t0, 1, h->flags, st); h->launches++; }
+    if (did_W) {
+        launch_rowsum_flag<T>((const T*)h->Wt + (int64_t)t0 * h->ldwt, t1 - t0, h->n, h->ldwt, h->sums, h->k + t0,
+                              h->world > 1 ? 0 : 2, h->flags, st);
+        h->launches++;
+        if (h->world > 1) {
+            NCK(g_nccl.AllReduce(h->sums + h->k + t0, h->sums + h->k + t0, (size_t)(t1 - t0), 8, 0, h->comm, st));
+            launch_flag_from_sums(h->sums, h->k + t0, t1 - t0, 2, h->flags, st);
+            h->launches += 2;
+        }
+    }
     return 0;
 }
 
@@ -994,6 +1021,7 @@ static int sp_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri
         if (sp_T_step<T>(h, W, Tm, t, p, S, st)) return 1;
         if (sp_W_step<T>(h, W, Tm, t, p, S, st)) return 1;
     }
+    if (sp_topic_sums<T>(h, Tm, t0, t1, true, true, st)) return 1;
     CKL();
     return 0;
 }
@@ -1020,6 +1048,7 @@ static int sp_sweeps(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_params
         sp_refresh<T>(h, true, false, W, st);
         for (int t = 0; t < k; ++t)
             if (sp_W_step<T>(h, W, Tm, t, p, S, st)) return 1;
+        if (sp_topic_sums<T>(h, Tm, 0, k, !p->fix_T, true, st)) return 1;
     }
     CKL();
     return 0;

@@ -279,6 +279,36 @@ void launch_vec_sum_flag(const T* v, int64_t len, int64_t stride, double* sums, 
     vec_sum_flag_kernel<T><<<1, 1024, 0, st>>>(v, len, stride, sums, slot, zero_flag, flags);
 }
 
+// sums[slot0 + r] = sum_i A[r*ld + i] for r < rows (one block per row, same fixed order as vec_sum_flag_kernel):
+// the per-topic sums of a whole sweep in one launch
+template <typename T>
+__global__ void __launch_bounds__(1024)
+rowsum_flag_kernel(const T* __restrict__ A, int64_t len, int64_t ld, double* __restrict__ sums, int slot0,
+                   int zero_flag, int* __restrict__ flags)
+{
+    __shared__ double red[32];
+    const T* __restrict__ v = A + (int64_t)blockIdx.x * ld;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += (double)v[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        sums[slot0 + blockIdx.x] = tot;
+        if (zero_flag && !(tot > 1e-10)) atomicOr(flags, zero_flag);
+        if (!isfinite(tot)) atomicOr(flags, 8);
+    }
+}
+
+template <typename T>
+void launch_rowsum_flag(const T* A, int rows, int64_t len, int64_t ld, double* sums, int slot0, int zero_flag,
+                        int* flags, cudaStream_t st)
+{
+    if (rows > 0) rowsum_flag_kernel<T><<<rows, 1024, 0, st>>>(A, len, ld, sums, slot0, zero_flag, flags);
+}
+
 template <typename T>
 __global__ void vec_scale_to_sum_kernel(T* __restrict__ v, int64_t len, int64_t stride,
                                         const double* __restrict__ sums, int slot, double s)
@@ -417,6 +447,7 @@ void launch_norms(const T* v, int64_t len, double* part, double* out, cudaStream
     template void launch_wrri_final<T>(const T*, const T*, int, int64_t, const SolveArgs&, T*, int64_t,     \
                                        T*, int64_t, int*, cudaStream_t);                                    \
     template void launch_vec_sum_flag<T>(const T*, int64_t, int64_t, double*, int, int, int*, cudaStream_t);\
+    template void launch_rowsum_flag<T>(const T*, int, int64_t, int64_t, double*, int, int, int*, cudaStream_t);\
     template void launch_vec_scale_to_sum<T>(T*, int64_t, int64_t, const double*, int, double, cudaStream_t);\
     template void launch_objective<T>(const T*, int64_t, const void*, int, int64_t, const T*, const T*,     \
                                       int64_t, int64_t, int, double*, int, double*, cudaStream_t);          \

@@ -53,6 +53,34 @@ def _universal_stopping_condition(obj_history, eps_stop=1e-4):
     return abs(obj_history[-1] - obj_history[-2]) <= eps_stop * abs(obj_history[0] - obj_history[1])
 
 
+def _bcast_scalar(comm, v):
+    """the same Python scalar on every rank of a row-sharded run (rank 0's)"""
+    import torch.distributed as dist
+    box = [v]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def _all_any(comm, flag):
+    """collective OR of a per-rank stop decision: the ranks must leave the sweep loop together, or the next
+    exchange hangs"""
+    if comm is None or getattr(comm, 'world', 1) <= 1:
+        return bool(flag)
+    import torch.distributed as dist
+    res = [None] * comm.world
+    dist.all_gather_object(res, bool(flag))
+    return any(res)
+
+
+def _all_mean(comm, v):
+    if comm is None or getattr(comm, 'world', 1) <= 1:
+        return v
+    import torch.distributed as dist
+    res = [None] * comm.world
+    dist.all_gather_object(res, float(v))
+    return float(np.mean(res))
+
+
 def _is_empty(a):
     return a is None or int(np.prod(np.shape(a))) == 0
 
@@ -116,16 +144,80 @@ def _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum
     return Wi.to(Xd.dtype), Ti.to(Xd.dtype)
 
 
+_STAGE = {'bufs': None, 'bytes': 0}
+_STAGE_CHUNK_BYTES = 32 << 20
+_STAGE_THREADS = 8
+
+
+def _stage_buffers(nbuf, nbytes):
+    """module-level pinned staging buffers (page-locking host memory costs ~0.1 s per GB: pay it once per process)"""
+    if _STAGE['bufs'] is None or len(_STAGE['bufs']) < nbuf or _STAGE['bytes'] < nbytes:
+        _STAGE['bufs'] = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+        _STAGE['bytes'] = nbytes
+    return _STAGE['bufs']
+
+
+def _pageable_to_device(t, device):
+    """Host -> device copy of a large PAGEABLE array (what a drop-in user passes) at close to the pinned rate:
+    row chunks are copied into a few pinned staging buffers by worker threads (tensor.copy_ releases the GIL) and
+    go to the device with asynchronous copies on a side stream, so the pageable -> pinned memcpy of one chunk
+    overlaps the DMA of the others.  A single pin_memory() of the whole array would cost a second full host copy
+    plus the page-locking of a data-sized allocation, serialised before the first byte moves."""
+    import threading
+    flat = t.reshape(-1).view(torch.uint8) if t.is_contiguous() else t.contiguous().reshape(-1).view(torch.uint8)
+    total = flat.numel()
+    out = torch.empty(t.shape, dtype=t.dtype, device=device)
+    oflat = out.reshape(-1).view(torch.uint8)
+    nthreads = max(1, min(_STAGE_THREADS, len(__import__('os').sched_getaffinity(0))))
+    bufs = _stage_buffers(2 * nthreads, _STAGE_CHUNK_BYTES)
+    nchunks = (total + _STAGE_CHUNK_BYTES - 1) // _STAGE_CHUNK_BYTES
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    errors = []
+
+    def worker(w):
+        try:
+            torch.cuda.set_device(device)
+            events = [None, None]
+            for j, c in enumerate(range(w, nchunks, nthreads)):
+                b = bufs[2 * w + (j & 1)]
+                if events[j & 1] is not None:
+                    events[j & 1].synchronize()            # the DMA that last read this buffer has finished
+                lo = c * _STAGE_CHUNK_BYTES
+                hi = min(total, lo + _STAGE_CHUNK_BYTES)
+                b[:hi - lo].copy_(flat[lo:hi])              # pageable -> pinned (GIL released)
+                with torch.cuda.stream(side):
+                    oflat[lo:hi].copy_(b[:hi - lo], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                events[j & 1] = ev
+            for ev in events:
+                if ev is not None:
+                    ev.synchronize()
+        except Exception as ex:                             # surfaced by the caller
+            errors.append(ex)
+
+    threads = [threading.Thread(target=worker, args=(w,)) for w in range(nthreads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
+    torch.cuda.current_stream(device).wait_stream(side)
+    return out
+
+
 def _to_device(a, device, dtype):
     if isinstance(a, torch.Tensor):
-        return a.to(device=device, dtype=dtype)
+        if a.device.type == 'cpu' and device.type == 'cuda' and a.dtype == dtype and not a.is_pinned() \
+                and a.numel() * a.element_size() >= (64 << 20) and a.layout == torch.strided:
+            return _pageable_to_device(a, device)
+        return a.to(device=device, dtype=dtype, non_blocking=a.device.type == 'cpu' and a.is_pinned())
     a = np.ascontiguousarray(a)
     t = torch.from_numpy(a)
-    if device.type == 'cuda' and t.numel() > (1 << 20):
-        try:
-            t = t.pin_memory()
-        except RuntimeError:
-            pass
+    if device.type == 'cuda' and t.dtype == dtype and not t.is_pinned() and t.numel() * t.element_size() >= (64 << 20):
+        return _pageable_to_device(t, device)
     return t.to(device=device, dtype=dtype, non_blocking=True)
 
 
@@ -179,12 +271,23 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
             raise NotImplementedError('fix_W=True is not available on row shards')
     if w_row_sum is not None and not np.isscalar(w_row_sum):
         raise NotImplementedError('vector w_row_sum is not on the device path')
+    sharded = comm is not None and getattr(comm, 'world', 1) > 1
+    if sharded:
+        # Row-sharded contract: every rank passes ITS rows of X / W_in / W_mat and the SAME T_in.
+        # An initialisation computed per shard would give every rank a different T replica (garbage, silently), so
+        # both factors must be given; T_in and random_state are then broadcast from rank 0 so that the replicas
+        # are bit-identical from sweep 0 whatever the caller passed.
+        if _is_empty(W_in) or _is_empty(T_in):
+            raise ValueError('row-sharded runs (comm=...) need W_in (the local rows) and T_in (replicated): an '
+                             'initialisation per shard would start the ranks from different T')
     if type(diagnostics) is not list:
         diagnostics = [diagnostics]
     if len(diagnostics) > 0:
         rtv['diagnostics'] = {f.__name__: [] for f in diagnostics}
     if random_state is None:
         random_state = int(time.time()) % 4294967296
+    if sharded:
+        random_state = _bcast_scalar(comm, random_state)
     t_global_start = time.time()
     max_time = max_time - 10                                     # nmf.py:333
     if n <= k:
@@ -260,6 +363,11 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         # np.maximum(W_in, 0) makes copies: the caller's arrays are never mutated (nmf.py:867-868)
         W = _to_device(W0, device, dtype).clamp(min=0).contiguous()
         T = _to_device(T0, device, dtype).clamp(min=0).contiguous()
+        if sharded:
+            import torch.distributed as dist
+            if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
+                T = T.clone()
+            dist.broadcast(T, src=0)
         if W.data_ptr() == (W0.data_ptr() if isinstance(W0, torch.Tensor) else 0):
             W = W.clone()
         if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
@@ -336,16 +444,26 @@ def _solve(engine, Xd, W, T, rtv, a):
 
     # sweeps can be batched into one library call when nothing on the host has to look at the state
     # in between (N sweeps in one call == N calls of one sweep, bit for bit)
+    comm = a['comm']
+    sharded = comm is not None and getattr(comm, 'world', 1) > 1
+    can_reset = reset_topic_method is not None and engine.order == 'rri' and not masked and not fix_T \
+        and not a['fix_W'] and not sharded
+    if reset_topic_method is not None and not can_reset and not fix_T and not a['fix_W']:
+        # the reference re-seeds an emptied topic (nmf.py:762-816); here that policy exists for the unmasked,
+        # unsharded interleaved order only.  Say so up front; an emptied topic then raises (see _raise_on_flags).
+        logger.info("reset_topic_method=%r is only applied with update_order='rri' on unmasked, unsharded data; "
+                    "on this engine an emptied topic raises instead of being re-seeded", reset_topic_method)
     per_sweep_host = bool(early_stop) or compute_obj_each_iter or bool(diagnostics) or \
-        (project_W_each_iter and w_row_sum is not None) or reset_topic_method is not None
+        (project_W_each_iter and w_row_sum is not None) or can_reset
     chunk = 1 if per_sweep_host else max(1, int(a['sweeps_per_call']))
-    can_reset = reset_topic_method is not None and engine.order == 'rri' and not masked
 
     iter_no = 0
     while iter_no < max_iter:
         if early_stop:                                                             # nmf.py:381-407
             if callable(early_stop):
-                this_score = early_stop(Xcb, host_view(W), host_view(T))
+                # row shards: every rank scores its own rows; the decision uses the mean over ranks so that all
+                # ranks revert and leave together
+                this_score = _all_mean(comm, early_stop(Xcb, host_view(W), host_view(T)))
             else:
                 this_score = obj_history[-1] if (compute_obj_each_iter and obj_history) else np.inf
             if this_score > last_score:
@@ -372,7 +490,11 @@ def _solve(engine, Xd, W, T, rtv, a):
             W.copy_(W_save)
             T.copy_(T_save)
             flags = _sweep_with_resets(engine, Xd, W, T, params, a, state)
-        _raise_on_flags(flags, engine)
+        if fix_T and reset_topic_method is not None:
+            # transform(): the reference would re-seed topic t (T row included!) when no new document uses it
+            # (nmf.py:796-816 runs under fix_T as well).  Here T is left alone and the column stays zero.
+            flags &= ~_lib.FLAG_ZERO_W
+        _raise_on_flags(flags, engine, reset_topic_method if not (can_reset or fix_T) else None)
         iter_no += ns
         if project_W_each_iter and not a['fix_W'] and w_row_sum is not None:      # nmf.py:481-484
             engine.project_rows_simplex(W, w_row_sum)
@@ -382,10 +504,11 @@ def _solve(engine, Xd, W, T, rtv, a):
         iter_cputime.extend([now] * ns)
         for f in diagnostics:                                                      # nmf.py:495-500
             rtv['diagnostics'][f.__name__].append(f(Xcb, host_view(W), host_view(T)))
-        if time.time() - t_global_start >= max_time:                               # nmf.py:506-508
+        # stop decisions are collective on row shards (a rank that left alone would hang the others' exchange)
+        if _all_any(comm, time.time() - t_global_start >= max_time):              # nmf.py:506-508
             break
         if compute_obj_each_iter and _universal_stopping_condition(obj_history, eps_stop):   # :510-514
-            break
+            break                       # (the objective is all-reduced: the same number on every rank)
     iter_cputime = [x - a['start_time'] for x in iter_cputime]
 
     if (not project_W_each_iter and w_row_sum is not None and not a['fix_W'] and a['do_final_project_W']):
@@ -461,7 +584,13 @@ def _sweep_fix_W(engine, W, T, a):
     return 0
 
 
-def _raise_on_flags(flags, engine):
+def _raise_on_flags(flags, engine, unapplied_reset=None):
+    if unapplied_reset is not None and flags & (_lib.FLAG_ZERO_T | _lib.FLAG_ZERO_W):
+        sT, sW = engine.topic_sums()
+        if np.any(sT <= 1e-10) or np.any(sW <= 1e-10):
+            raise ValueError("a topic emptied (sum <= 1e-10) and reset_topic_method=%r is not applied on this engine "
+                             "(resets exist for update_order='rri' on unmasked, unsharded data; nmf.py:762-816): "
+                             "use that mode, other initial factors, or reset_topic_method=None" % (unapplied_reset,))
     if flags & _lib.FLAG_UNBOUNDED:
         # optimization.py:60-67 / :76-77 -> _unbounded_objective (:105-107)
         raise ValueError('Minimum objective is unbounded. (a denominator became <= 0 with no upper bound; '

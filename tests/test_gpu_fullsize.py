@@ -15,7 +15,7 @@ def cfg3(cuda_device):
         pytest.skip('needs ~40 GB of device memory')
     import bench
     cfg = dict(bench.CONFIGS['cfg3'])
-    X, W0, T0 = bench.gen_shard(torch, cfg, cfg['n'], 0, cuda_device, seed=0)
+    X, W0, T0 = bench.gen_shard(torch, cfg, cfg["n"], 0, cuda_device)
     yield X, W0, T0
     del X, W0, T0
     torch.cuda.empty_cache()

@@ -8,7 +8,7 @@ import rri_nmf_b200 as R
 sweeps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 dev = torch.device('cuda:0')
 cfg = dict(bench.CONFIGS['cfg3'])
-X, W0, T0 = bench.gen_shard(torch, cfg, cfg['n'], 0, dev, seed=0)
+X, W0, T0 = bench.gen_shard(torch, cfg, cfg["n"], 0, dev)
 res = {}
 for math in ('tf32', 'ieee'):
     eng = R.RRIEngine(X, 64, order='hals', math=math)
