@@ -634,8 +634,10 @@ static int check_params(rri_handle_t h, const rri_params_t* p)
     if (p->fix_W && p->fix_T) return fail("fix_W and fix_T both set: nothing to update");
     if (p->fix_W) return fail("fix_W=True is not supported on the device path (the reference's T-only sweep also rescales W, nmf.py:450-452)");
     if (p->simplex_T) {
-        if (h->mk != MK_NONE) return fail("project_T_each_iter is not supported together with W_mat on the device path");
-        if (h->order != RRI_ORDER_RRI) return fail("project_T_each_iter couples the columns of T: it needs update_order='rri'");
+        // unmasked: Euclidean projection of the row onto the simplex (optimization.py:58-59); masked / observed
+        // entries: the vector-c branch rescales the clipped solution to the sum (optimization.py:85-87)
+        if (h->mk == MK_NONE && h->order != RRI_ORDER_RRI)
+            return fail("project_T_each_iter couples the columns of T: it needs update_order='rri'");
         if (!(p->ub_t > 0)) return fail("simplex_T needs t_row_sum > 0");
     }
     return 0;
@@ -827,6 +829,18 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
 // -------------------------------------------------------------------------------------------------
 // masked WRRI (both orders)
 // -------------------------------------------------------------------------------------------------
+// vector-c solve with a sum constraint (optimization.py:85-87): x <- s x / sum(x), with sum(x) = sums[t] taken
+// after the ub clip; the copy the next pass reads (row2, stride ld2) is rescaled as well, and sums[t] becomes the
+// sum AFTER the rescaling -- the nt1 that the zero-topic test of nmf.py:757 sees
+template <typename T>
+static void scale_row_to_sum(rri_handle_t h, T* row, T* row2, int64_t ld2, int t, const rri_params_t* p, cudaStream_t st)
+{
+    launch_vec_scale_to_sum<T>(row, h->d, 1, h->sums, t, p->ub_t, st);
+    if (row2) { launch_vec_scale_to_sum<T>(row2, h->d, ld2, h->sums, t, p->ub_t, st); h->launches++; }
+    launch_vec_sum_flag<T>(row, h->d, 1, h->sums, t, 1, h->flags, st);
+    h->launches += 2;
+}
+
 template <typename T>
 static int wrri_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, cudaStream_t st)
 {
@@ -855,8 +869,9 @@ static int wrri_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p
     T* tp2 = h->wtc ? (T*)wrri_tc_Tp(h->wtc) + t : nullptr;       // keep the padded T' operand in step
     launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), Tm + (int64_t)t * d, 1, tp2,
                          h->wtc ? wrri_tc_KP(h->wtc) : 0, h->flags, st);
-    launch_vec_sum_flag<T>(Tm + (int64_t)t * d, d, 1, h->sums, t, 1, h->flags, st);
+    launch_vec_sum_flag<T>(Tm + (int64_t)t * d, d, 1, h->sums, t, p->simplex_T ? 0 : 1, h->flags, st);
     h->launches += 2;
+    if (p->simplex_T) scale_row_to_sum<T>(h, Tm + (int64_t)t * d, tp2, h->wtc ? wrri_tc_KP(h->wtc) : 0, t, p, st);
     return 0;
 }
 
@@ -942,7 +957,11 @@ static int sp_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p, 
     }
     launch_wrri_final<T>(nu, de, parts, d, solve_args(p, true), trow, 1, (T*)h->Tt + t, h->sp_ldt, h->flags, st);
     h->launches++;
-    if (!h->sp_batched_sums) { launch_vec_sum_flag<T>(trow, d, 1, h->sums, t, 1, h->flags, st); h->launches++; }
+    if (!h->sp_batched_sums || p->simplex_T) {
+        launch_vec_sum_flag<T>(trow, d, 1, h->sums, t, p->simplex_T ? 0 : 1, h->flags, st);
+        h->launches++;
+    }
+    if (p->simplex_T) scale_row_to_sum<T>(h, trow, (T*)h->Tt + t, h->sp_ldt, t, p, st);
     S.csc = SpPending{wt, wt, told, trow};       // w_t (told - tnew)'; merged with the W-step's change if one follows
     S.told_cur = told;
     S.ct++;
