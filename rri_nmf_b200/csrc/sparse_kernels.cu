@@ -432,84 +432,6 @@ sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restri
     }
 }
 
-// CANDIDATE for the next round (not the default, not yet run on a GPU; RRI_SP_PASS_V2=1 selects it): the same pass
-// with two entries per lane and load -- one 32-bit load for two 16-bit indices, one 64-bit load for two residuals --
-// i.e. 16 entries per lane and 512 per warp in flight per trip (most sub-segments then finish in ONE trip instead
-// of two dependent ones), and with the next sub-segment's bounds and scalars requested before the current stream.
-// Needs idx16 and residual arrays padded by two elements (rri_bind_csr does that) and fp32.
-template <bool HASW, int U>
-__global__ void __launch_bounds__(1024, 1)
-sp_pass_blocked2_kernel(const int64_t* __restrict__ ptr2, const uint16_t* __restrict__ idx16, float* __restrict__ E,
-                        const float* __restrict__ wgt, const Quad<float>* __restrict__ Q,
-                        const float* __restrict__ own_po, const float* __restrict__ own_pn,
-                        const float* __restrict__ own_cur, float* __restrict__ own_save,
-                        float* __restrict__ numer_part, float* __restrict__ denom_part, int64_t nseg, int nblk, int nb,
-                        int64_t nother, int chunks)
-{
-    extern __shared__ __align__(16) unsigned char sp_smem[];
-    Quad<float>* __restrict__ qs = reinterpret_cast<Quad<float>*>(sp_smem);
-    const int b = (int)(blockIdx.x % (unsigned)nblk), c = (int)(blockIdx.x / (unsigned)nblk);
-    const int64_t base = (int64_t)b * nb;
-    const int cnt = (int)((nother - base) < (int64_t)nb ? (nother - base) : (int64_t)nb);
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) qs[i] = Q[base + i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int64_t s0, s1;
-    part_range(nseg, chunks, c, s0, s1);
-    const bool apply = own_po != nullptr;
-    const int64_t pstride = (int64_t)nblk + 1;
-    int64_t s = s0 + warp;
-    int64_t beg = 0, end = 0;
-    float opo = 0.f, opn = 0.f, oc = 0.f;
-    if (s < s1) {
-        beg = ptr2[s * pstride + b]; end = ptr2[s * pstride + b + 1];
-        opo = apply ? own_po[s] : 0.f; opn = apply ? own_pn[s] : 0.f; oc = own_cur[s];
-    }
-    while (s < s1) {
-        const int64_t sn = s + nwarps;
-        int64_t nbeg = 0, nend = 0;
-        float nopo = 0.f, nopn = 0.f, noc = 0.f;
-        if (sn < s1) {                               // off the critical path of this sub-segment
-            nbeg = ptr2[sn * pstride + b]; nend = ptr2[sn * pstride + b + 1];
-            nopo = apply ? own_po[sn] : 0.f; nopn = apply ? own_pn[sn] : 0.f; noc = own_cur[sn];
-        }
-        float num = 0.f, den = 0.f;
-        const int64_t a0 = beg & ~(int64_t)1;        // pairs start on an even entry: 4- / 8-byte aligned loads
-        for (int64_t pb = a0; pb < end; pb += 64 * U) {
-            uint32_t qp[U]; float2 ev[U]; float m0[U], m1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t p = pb + u * 64 + 2 * lane;          // entries p and p + 1
-                const bool any = p < end;
-                qp[u] = any ? *reinterpret_cast<const uint32_t*>(idx16 + p) : 0u;
-                ev[u] = any ? *reinterpret_cast<const float2*>(E + p) : make_float2(0.f, 0.f);
-                m0[u] = (HASW && any && p >= beg) ? wgt[p] : 1.f;
-                m1[u] = (HASW && p + 1 < end) ? wgt[p + 1] : 1.f;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t p = pb + u * 64 + 2 * lane;
-                if (p >= beg && p < end) {
-                    const Quad<float> qq = qs[qp[u] & 0xffffu];
-                    sp_entry<float, HASW>(ev[u].x, qq, m0[u], opo, opn, oc, apply, E + p, num, den);
-                }
-                if (p + 1 < end) {                                  // (p + 1 >= beg holds for every p >= a0)
-                    const Quad<float> qq = qs[qp[u] >> 16];
-                    sp_entry<float, HASW>(ev[u].y, qq, m1[u], opo, opn, oc, apply, E + p + 1, num, den);
-                }
-            }
-        }
-        num = warp_sum(num);
-        den = warp_sum(den);
-        if (lane == 0) {
-            numer_part[(int64_t)b * nseg + s] = num;
-            denom_part[(int64_t)b * nseg + s] = den;
-            if (b == 0) own_save[s] = oc;
-        }
-        s = sn; beg = nbeg; end = nend; opo = nopo; opn = nopn; oc = noc;
-    }
-}
-
 // ptr2[s][b] = first entry of segment s whose index is >= b * nb   (b = 0..nblk)
 __global__ void sp_subptr_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nseg, int nblk,
                                  int nb, int64_t* __restrict__ ptr2)
@@ -575,19 +497,6 @@ int launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* 
         if (chunks < 1) chunks = 1;
         if ((int64_t)chunks * 32 > s.nseg) chunks = (int)((s.nseg + 31) / 32);
         if (chunks < 1) chunks = 1;
-        if constexpr (sizeof(T) == 4) {
-            static const bool v2 = [] { const char* e = getenv("RRI_SP_PASS_V2"); return e && *e == '1'; }();
-            if (v2 && s.idx16) {
-                auto k2 = w ? sp_pass_blocked2_kernel<true, 4> : sp_pass_blocked2_kernel<false, 8>;
-                if (smem > 48 * 1024) cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-                k2<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx16, (float*)E, (const float*)w,
-                                                                    (const Quad<float>*)Q, (const float*)own_po,
-                                                                    (const float*)own_pn, (const float*)own_cur,
-                                                                    (float*)own_save, (float*)numer, (float*)denom, s.nseg,
-                                                                    s.nblk, s.nb, s.nother, chunks);
-                return s.nblk;
-            }
-        }
         auto kern = w ? sp_pass_blocked_kernel<T, true, U> : sp_pass_blocked_kernel<T, false, U>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         kern<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save, numer,
