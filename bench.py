@@ -348,6 +348,19 @@ def main_ours(args):
                 'sweep_effective_gbs': passes * alg_bytes / (ms_per_step * 1e-3) / 1e9,
                 'kernel_share_of_step': passes * kms / ms_per_step}
 
+    if args.order == 'hals':
+        # whole half-steps (contraction + Gram + exchange + update), CUDA events; what is not the contraction is the
+        # fixed cost that does not shrink with the shard
+        try:
+            Wc, Tc = W.clone(), T.clone()
+            th, wh = eng.profile_kernel('t_half', Wc, Tc, 5), eng.profile_kernel('w_half', Wc, Tc, 5)
+            gt, gw = eng.profile_kernel('gemm_t', Wc, Tc, 5), eng.profile_kernel('gemm_w', Wc, Tc, 5)
+            roofline['half_steps_ms'] = {'t_half': th, 'w_half': wh, 'gemm_t': gt, 'gemm_w': gw,
+                                         't_half_minus_contraction': th - gt, 'w_half_minus_contraction': wh - gw}
+            del Wc, Tc
+        except Exception as ex:
+            roofline['half_steps_ms'] = {'error': repr(ex)[:200]}
+
     # ---- e2e: the public call with HOST buffers, copies inside the timed region.  Two figures: pinned host arrays
     # (the headline e2e) and plain pageable NumPy arrays (what a drop-in user passes; nmf() stages them through
     # its own pinned chunk buffers)

@@ -152,7 +152,9 @@ int rri_gemm_nt(rri_handle_t h, const void* A_dev, int64_t lda, const void* B_de
  * `stream` between two CUDA events and return the average launch duration in milliseconds.
  *   which = 0: the rri-order fused pass (y = X T_t', p = w_t' X)      -- reads X[n,d] once
  *   which = 1: the W half-step contraction  X T'  (n x d -> n x k)     -- reads X once
- *   which = 2: the T half-step contraction  X' W  (d x n -> d x k)     -- reads X' once (hals handles) */
+ *   which = 2: the T half-step contraction  X' W  (d x n -> d x k)     -- reads X' once (hals handles)
+ *   which = 3 / 4: one whole T / W half-step of the block order (contraction, Gram, exchange, update); these
+ *              advance W_dev / T_dev and, on row shards, are collective (every rank calls with the same iters) */
 int rri_profile_kernel(rri_handle_t h, int32_t which, const void* W_dev, const void* T_dev, int32_t iters,
                        float* avg_ms_host, void* stream);
 

@@ -103,6 +103,23 @@ extern "C" int rri_nccl_comm_destroy(void* comm)
 // -------------------------------------------------------------------------------------------------
 // handle
 // -------------------------------------------------------------------------------------------------
+// Exchange buffers and their peer mappings outlive the handle: cudaMalloc + CUDA-IPC export / open of a fresh buffer
+// cost ~0.2 s per engine (longer than 40 sweeps of the headline configuration at two GPUs), and every nmf() call
+// creates a new engine.  A destroyed handle parks its buffer here; the next handle of the same geometry on the same
+// device takes it over, and when all ranks present the same IPC handles again the mappings are reused as they are
+// (the epoch counter continues, so stale flags can never satisfy a wait).  Entries are only released by
+// rri_cache_trim -- to be called on all ranks together -- so no rank ever frees a buffer a peer still has mapped.
+struct PeerGroup {
+    bool used = false;
+    int device = -1, world = 0, rank = 0;
+    void* xbuf = nullptr; size_t bytes = 0;
+    void* peer_base[16] = {nullptr}; bool peer_open[16] = {false};
+    char handles[16 * 64] = {0};
+    bool mapped = false;
+    unsigned epoch = 0;
+};
+
+
 struct rri_handle_s {
     int64_t n = 0, d = 0;
     int k = 0, dtype = 0, math = 0, order = 0, device = 0, sm_count = 148;
@@ -112,16 +129,20 @@ struct rri_handle_s {
     const void* M = nullptr; int mk = 0; int64_t ldm = 0;
     // comm
     void* comm = nullptr; int rank = 0, world = 1;
-    // peer-memory exchange of the T half-step statistic (multi-GPU hals): every rank exports one buffer
-    //   [2 epochs][d*k + k*k] elements + flag word; all ranks map all buffers (CUDA IPC)
+    // peer-memory exchange of the T half-step (multi-GPU hals): every rank exports one buffer
+    //   [2 epochs][d*k + k*k] partial statistic | T' replica [d,k] | T replica [k,ldtk] | slice sums [16][k] | flags
+    // and all ranks map all buffers (CUDA IPC); see hals_kernels.cu: peer_update_rows_kernel
     void* xbuf = nullptr; size_t xbuf_bytes = 0, xslot_elems = 0;
+    size_t x_off_tt = 0, x_off_tk = 0, x_off_tsum = 0, x_off_flags = 0;
+    int64_t ldtk = 0;
     void* peer_base[16] = {nullptr}; bool peer_open[16] = {false};
-    void** d_peerP = nullptr;      // device [2][world] pointers to the ranks' partial slots  [X_i'W_i | W_i'W_i]
-    void** d_peerR = nullptr;      // device [2][world] pointers to the ranks' reduced slots
-    unsigned** d_peerFlag = nullptr;   // device [2][world] pointers to the two epoch flags of every rank
+    void* Tt_own = nullptr;            // the handle's private T' (used again when the exchange is switched off)
     unsigned epoch = 0;
-    bool p2p = false;
+    bool p2p = false, peer_mapped = false;
     int* p2p_err = nullptr;
+    char handles[16 * 64] = {0};       // the IPC handles the current mappings were opened from
+    PeerGroup parked; bool have_parked = false;     // parked group taken over by rri_peer_export
+    unsigned* counters = nullptr;      // [8] arrival counters of the "last block finalises" kernels (zero between launches)
     // workspace
     std::vector<void*> allocs;
     int64_t ws_bytes = 0, launches = 0;
@@ -194,7 +215,8 @@ extern "C" int rri_create(rri_handle_t* out, int64_t n_local, int64_t d, int32_t
     h->n = n_local; h->d = d; h->k = k; h->dtype = dtype; h->math = math; h->order = order;
     h->device = device; h->sm_count = prop.multiProcessorCount;
     h->es = dtype == RRI_F32 ? 4 : 8;
-    if (ws_alloc(h, (void**)&h->sums, sizeof(double) * 2 * k) || ws_alloc(h, (void**)&h->flags, sizeof(int) * 4)) {
+    if (ws_alloc(h, (void**)&h->sums, sizeof(double) * 2 * k) || ws_alloc(h, (void**)&h->flags, sizeof(int) * 4) ||
+        ws_alloc(h, (void**)&h->counters, sizeof(unsigned) * 8)) {
         rri_destroy(h);
         return 1;
     }
@@ -203,13 +225,13 @@ extern "C" int rri_create(rri_handle_t* out, int64_t n_local, int64_t d, int32_t
     return 0;
 }
 
+static void peer_release(rri_handle_t h);
+
 extern "C" int rri_destroy(rri_handle_t h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    for (int r = 0; r < 16; ++r)
-        if (h->peer_open[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
-    if (h->xbuf) cudaFree(h->xbuf);
+    peer_release(h);
     for (void* p : h->allocs) cached_free(p);
     if (h->tf32) tf32_gemm_destroy(h->tf32);
     if (h->wtc) wrri_tc_destroy(h->wtc);
@@ -229,72 +251,28 @@ extern "C" int rri_set_comm(rri_handle_t h, void* nccl_comm, int32_t rank, int32
 }
 
 // -------------------------------------------------------------------------------------------------
-// peer-memory exchange (fused replacement of the NCCL all-reduce in the block-order T half-step)
+// peer-memory exchange (the NCCL all-reduce of the block-order T half-step replaced by NVLink loads / stores inside
+// the update kernel: hals_kernels.cu peer_update_rows_kernel)
 // -------------------------------------------------------------------------------------------------
-__global__ void peer_signal_kernel(unsigned* flag, unsigned epoch)
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static PeerGroup g_groups[64];
+
+static PeerGroup* group_take(int device, size_t bytes)
 {
-    // everything this rank wrote into its exchange slot (previous kernels of this stream) is made visible
-    // system-wide before the epoch flag is published
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+    for (PeerGroup& g : g_groups)
+        if (g.used && g.device == device && g.bytes == bytes) { g.used = false; return &g; }
+    return nullptr;
+}
+static PeerGroup* group_slot()
+{
+    for (PeerGroup& g : g_groups) if (!g.used) return &g;
+    return nullptr;
 }
 
-__global__ void peer_wait_kernel(unsigned* const* flags, int world, unsigned epoch, int* err)
+static bool peer_rank_supported(rri_handle_t h)
 {
-    const int r = threadIdx.x;
-    if (r < world) {
-        const unsigned* f = flags[r];
-        const long long t0 = clock64();
-        for (;;) {
-            unsigned v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if ((int)(v - epoch) >= 0) break;
-            if (clock64() - t0 > 200000000000LL) {     // ~100 s: a lost peer must not hang the GPU for ever
-                atomicExch(err, 1 + r);
-                __trap();
-            }
-            __nanosleep(200);
-        }
-    }
-    __threadfence_system();
-}
-
-// Two-shot all-reduce over peer memory.  Rank r owns the r-th slice of the statistic vector: it adds the
-// slice of every rank's partial slot in rank order (7 remote reads) and stores the result into every rank's
-// reduced slot (7 remote writes).  Each rank moves 2*(g-1)/g of the vector over NVLink, like a ring, but in
-// two latency hops; the fixed summation order makes the result bit-identical on all ranks.
-template <typename T>
-__global__ void __launch_bounds__(256)
-peer_reduce_scatter_gather_kernel(T* const* partial, T* const* reduced, int world, int rank, int64_t len)
-{
-    using V = typename Vec<T>::type;
-    constexpr int VN = Vec<T>::N;
-    const int64_t nvec = len / VN;                 // len is padded to a multiple of 64 elements
-    const int64_t per = (nvec + world - 1) / world;
-    const int64_t lo = per * rank, hi = (lo + per) < nvec ? (lo + per) : nvec;
-    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
-        V v[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r)
-            if (r < world) v[r] = reinterpret_cast<const V*>(partial[r])[i];
-        T acc[VN];
-        unpack(v[0], acc);
-#pragma unroll
-        for (int r = 1; r < 16; ++r)
-            if (r < world) {
-                T t[VN];
-                unpack(v[r], t);
-#pragma unroll
-                for (int q = 0; q < VN; ++q) acc[q] += t[q];
-            }
-        V out;
-        T* o = reinterpret_cast<T*>(&out);
-#pragma unroll
-        for (int q = 0; q < VN; ++q) o[q] = acc[q];
-#pragma unroll
-        for (int r = 0; r < 16; ++r)
-            if (r < world) reinterpret_cast<V*>(reduced[r])[i] = out;
-    }
+    return h->dtype == RRI_F32 ? h->k <= 128 : h->k <= 64;      // the thread-per-row update kernel
 }
 
 extern "C" int rri_peer_export(rri_handle_t h, char handle_out[64])
@@ -302,13 +280,29 @@ extern "C" int rri_peer_export(rri_handle_t h, char handle_out[64])
     if (!h) return fail("null handle");
     if (!h->X) return fail("rri_bind has not been called");
     if (h->order != RRI_ORDER_HALS || h->mk != MK_NONE) return fail("the peer-memory exchange serves unmasked hals handles");
+    if (!peer_rank_supported(h)) return fail("the fused peer-memory T update supports k <= 128 (f32) / 64 (f64)");
     CK(cudaSetDevice(h->device));
     if (!h->xbuf) {
+        const size_t es = h->es;
+        const int64_t v = 16 / (int64_t)es;
+        h->ldtk = (h->d + v - 1) / v * v;
         h->xslot_elems = ((size_t)h->d * h->k + (size_t)h->k * h->k + 63) / 64 * 64;
-        h->xbuf_bytes = 4 * h->xslot_elems * h->es + 256;
-        CK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
-        CK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
-        CK(cudaDeviceSynchronize());
+        h->x_off_tt = round_up(2 * h->xslot_elems * es, 256);
+        h->x_off_tk = round_up(h->x_off_tt + (size_t)h->d * h->k * es, 256);
+        h->x_off_tsum = round_up(h->x_off_tk + (size_t)h->k * h->ldtk * es, 256);
+        h->x_off_flags = round_up(h->x_off_tsum + (size_t)16 * h->k * es, 256);
+        h->xbuf_bytes = h->x_off_flags + 2 * 16 * 32 * sizeof(unsigned);
+        if (PeerGroup* g = group_take(h->device, h->xbuf_bytes)) {
+            // a parked buffer of the same geometry: same IPC handle as before, mappings kept for rri_peer_import
+            h->xbuf = g->xbuf;
+            h->parked = *g;
+            h->have_parked = true;
+            *g = PeerGroup();
+        } else {
+            CK(cudaMalloc(&h->xbuf, h->xbuf_bytes));
+            CK(cudaMemset(h->xbuf, 0, h->xbuf_bytes));
+            CK(cudaDeviceSynchronize());
+        }
     }
     cudaIpcMemHandle_t mh;
     CK(cudaIpcGetMemHandle(&mh, h->xbuf));
@@ -323,6 +317,25 @@ extern "C" int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank
     if (!h->xbuf) return fail("rri_peer_export must be called first");
     if (world < 2 || world > 16 || rank < 0 || rank >= world) return fail("bad rank/world %d/%d", rank, world);
     CK(cudaSetDevice(h->device));
+    if (h->have_parked) {
+        PeerGroup& g = h->parked;
+        h->have_parked = false;
+        if (g.mapped && g.world == world && g.rank == rank && memcmp(g.handles, handles, (size_t)64 * world) == 0) {
+            // every rank came back with the buffer it had: nothing to map, the flags continue from the old epoch
+            for (int r = 0; r < 16; ++r) { h->peer_base[r] = g.peer_base[r]; h->peer_open[r] = g.peer_open[r]; }
+            memcpy(h->handles, handles, (size_t)64 * world);
+            if (!h->p2p_err && ws_alloc(h, (void**)&h->p2p_err, sizeof(int))) return 1;
+            CK(cudaStreamSynchronize(0));
+            h->rank = rank; h->world = world; h->epoch = g.epoch; h->p2p = false; h->peer_mapped = true;
+            return 0;
+        }
+        // some rank has a new buffer: drop the old mappings, restart the flags of this one
+        for (int r = 0; r < 16; ++r)
+            if (g.peer_open[r] && g.peer_base[r]) cudaIpcCloseMemHandle(g.peer_base[r]);
+        CK(cudaMemset((char*)h->xbuf + h->x_off_flags, 0, 2 * 16 * 32 * sizeof(unsigned)));
+        CK(cudaDeviceSynchronize());
+    }
+    memcpy(h->handles, handles, (size_t)64 * world);
     for (int r = 0; r < world; ++r) {
         if (r == rank) { h->peer_base[r] = h->xbuf; continue; }
         cudaIpcMemHandle_t mh;
@@ -335,25 +348,33 @@ extern "C" int rri_peer_import(rri_handle_t h, const char* handles, int32_t rank
         }
         h->peer_base[r] = p; h->peer_open[r] = true;
     }
-    std::vector<void*> pp(2 * world), pr(2 * world);
-    std::vector<unsigned*> pf(2 * world);
-    for (int r = 0; r < world; ++r) {
-        char* base = (char*)h->peer_base[r];
-        for (int b = 0; b < 2; ++b) {
-            pp[b * world + r] = base + (size_t)(2 * b) * h->xslot_elems * h->es;
-            pr[b * world + r] = base + (size_t)(2 * b + 1) * h->xslot_elems * h->es;
-            pf[b * world + r] = (unsigned*)(base + 4 * h->xslot_elems * h->es) + 32 * b;    // 128 bytes apart
-        }
-    }
-    if (ws_alloc(h, (void**)&h->d_peerP, sizeof(void*) * 2 * world) || ws_alloc(h, (void**)&h->d_peerR, sizeof(void*) * 2 * world) ||
-        ws_alloc(h, (void**)&h->d_peerFlag, sizeof(void*) * 2 * world) || ws_alloc(h, (void**)&h->p2p_err, sizeof(int)))
-        return 1;
-    CK(cudaMemcpy(h->d_peerP, pp.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_peerR, pr.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(h->d_peerFlag, pf.data(), sizeof(void*) * 2 * world, cudaMemcpyHostToDevice));
+    if (!h->p2p_err && ws_alloc(h, (void**)&h->p2p_err, sizeof(int))) return 1;
     CK(cudaStreamSynchronize(0));
     h->rank = rank; h->world = world; h->epoch = 0; h->p2p = false;     // enabled by rri_peer_enable on ALL ranks
+    h->peer_mapped = true;
     return 0;
+}
+
+// parks the exchange buffer and its mappings for the next handle (or really releases them when the table is full)
+static void peer_release(rri_handle_t h)
+{
+    if (!h->xbuf) return;
+    if (h->have_parked) {                       // exported from a parked group but never imported: put it back
+        if (PeerGroup* g = group_slot()) { *g = h->parked; g->used = true; h->xbuf = nullptr; h->have_parked = false; return; }
+    }
+    PeerGroup* g = group_slot();
+    if (g) {
+        g->used = true; g->device = h->device; g->world = h->world; g->rank = h->rank;
+        g->xbuf = h->xbuf; g->bytes = h->xbuf_bytes; g->mapped = h->peer_mapped; g->epoch = h->epoch;
+        for (int r = 0; r < 16; ++r) { g->peer_base[r] = h->peer_base[r]; g->peer_open[r] = h->peer_open[r]; }
+        memcpy(g->handles, h->handles, sizeof(g->handles));
+    } else {
+        for (int r = 0; r < 16; ++r)
+            if (h->peer_open[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+        cudaFree(h->xbuf);
+    }
+    h->xbuf = nullptr; h->peer_mapped = false;
+    for (int r = 0; r < 16; ++r) { h->peer_open[r] = false; h->peer_base[r] = nullptr; }
 }
 
 extern "C" int rri_peer_close(rri_handle_t h)
@@ -361,19 +382,54 @@ extern "C" int rri_peer_close(rri_handle_t h)
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->device));
     h->p2p = false;
-    for (int r = 0; r < 16; ++r) {
-        if (h->peer_open[r] && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
-        h->peer_open[r] = false; h->peer_base[r] = nullptr;
-    }
+    if (h->Tt_own) { h->Tt = h->Tt_own; h->Tt_own = nullptr; }
+    peer_release(h);
     return 0;
 }
 
 extern "C" int rri_peer_enable(rri_handle_t h, int32_t on)
 {
     if (!h) return fail("null handle");
-    if (on && !h->d_peerP) return fail("rri_peer_import has not succeeded on this rank");
+    if (on && !h->peer_mapped) return fail("rri_peer_import has not succeeded on this rank");
     h->p2p = on != 0;
+    // with the exchange on, the T' copy of this handle IS its replica inside the exchange buffer (the peers write
+    // the rows they own straight into it)
+    if (h->p2p) {
+        if (!h->Tt_own) h->Tt_own = h->Tt;
+        h->Tt = (char*)h->xbuf + h->x_off_tt;
+    } else if (h->Tt_own) {
+        h->Tt = h->Tt_own; h->Tt_own = nullptr;
+    }
     return 0;
+}
+
+// rows of T' (columns of T) that rank r updates in the fused exchange: 128-row blocks dealt out evenly
+static void peer_row_range(int64_t d, int world, int r, int64_t& lo, int64_t& hi)
+{
+    const int64_t nb = (d + 127) / 128;
+    const int64_t q = nb / world, rem = nb % world;
+    const int64_t b0 = q * r + (r < rem ? r : rem), b1 = b0 + q + (r < rem ? 1 : 0);
+    lo = b0 * 128 < d ? b0 * 128 : d;
+    hi = b1 * 128 < d ? b1 * 128 : d;
+}
+
+static PeerExchange peer_args(rri_handle_t h, unsigned epoch)
+{
+    PeerExchange px;
+    memset(&px, 0, sizeof(px));
+    px.world = h->world; px.rank = h->rank; px.epoch = epoch; px.ldtk = h->ldtk; px.err = h->p2p_err;
+    peer_row_range(h->d, h->world, h->rank, px.row_lo, px.row_hi);
+    const int b = (int)(epoch & 1u);
+    for (int r = 0; r < h->world; ++r) {
+        char* base = (char*)h->peer_base[r];
+        px.part[r] = base + (size_t)b * h->xslot_elems * h->es;
+        px.Tt[r] = base + h->x_off_tt;
+        px.Tk[r] = base + h->x_off_tk;
+        px.tsum[r] = base + h->x_off_tsum;
+        px.flag1[r] = (unsigned*)(base + h->x_off_flags);
+        px.flag2[r] = (unsigned*)(base + h->x_off_flags) + 16 * 32;
+    }
+    return px;
 }
 
 static int allreduce(rri_handle_t h, void* buf, size_t count, cudaStream_t st)
@@ -721,13 +777,16 @@ static int rri_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, bool fir
 // -------------------------------------------------------------------------------------------------
 // hals order, unmasked
 // -------------------------------------------------------------------------------------------------
+// C = A B' over the data (A = X or X'), plus -- TF32 path, G != null -- the Gram matrix G = B B' of the factor as one
+// more row tile of the same launch
 template <typename T>
 static int contraction(rri_handle_t h, const T* A, int64_t lda, const T* B, int64_t ldb, T* Cpart,
-                       int64_t M, int N, int64_t K, int splits, cudaStream_t st)
+                       int64_t M, int N, int64_t K, int splits, cudaStream_t st, T* G = nullptr)
 {
     if (h->math == RRI_MATH_TF32) {
         std::string err;
-        int nl = tf32_gemm_run(h->tf32, (const float*)A, lda, (const float*)B, ldb, (float*)Cpart, N, M, N, K, st, err);
+        int nl = tf32_gemm_run(h->tf32, (const float*)A, lda, (const float*)B, ldb, (float*)Cpart, N, M, N, K, st, err,
+                               G ? (const float*)B : nullptr, ldb, G ? N : 0, (float*)G, N);
         if (nl < 0) return fail("tf32 contraction failed: %s", err.c_str());
         h->launches += nl;
     } else {
@@ -737,28 +796,31 @@ static int contraction(rri_handle_t h, const T* A, int64_t lda, const T* B, int6
     return 0;
 }
 
+// the Gram matrix of a half-step: on the tensor cores inside the contraction launch (TF32 math, RRI_TC_GRAM=0 to
+// switch off), otherwise the IEEE gram_kernel + fixed-order reduce
+static bool gram_in_contraction(rri_handle_t h)
+{
+    static const bool off = [] { const char* e = getenv("RRI_TC_GRAM"); return e && *e == '0'; }();
+    return h->math == RRI_MATH_TF32 && !off;
+}
+
 template <typename T>
-static int hals_W_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, bool recompute, cudaStream_t st)
+static int hals_W_half(rri_handle_t h, T* W, const T* Tk, int64_t ldtk, const rri_params_t* p, bool recompute, cudaStream_t st)
 {
     const int k = h->k;
     const int64_t n = h->n, d = h->d;
     if (recompute) {
-        // H = T T' from the d x k transposed copy, C2 = X T'
-        launch_gram<T>((const T*)h->Tt, d, k, (T*)h->gram_part, h->gchunks_t, (T*)h->Hm, st);
-        h->launches += 2;
-        if (contraction<T>(h, (const T*)h->X, h->ldx, Tm, d, (T*)h->Cpart, n, k, d, h->splits_w, st)) return 1;
+        // C2 = X T' and H = T T' (from the d x k transposed copy, or as the Gram tile of the contraction)
+        const bool tc_gram = gram_in_contraction(h);
+        if (!tc_gram) { launch_gram<T>((const T*)h->Tt, d, k, (T*)h->gram_part, h->gchunks_t, (T*)h->Hm, st); h->launches += 2; }
+        if (contraction<T>(h, (const T*)h->X, h->ldx, Tk, ldtk, (T*)h->Cpart, n, k, d, h->splits_w, st, tc_gram ? (T*)h->Hm : nullptr)) return 1;
     }
     const int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_w;
+    // the zero-column test of nmf.py:793 is over ALL rows: with row shards the sums are all-reduced once per call
     launch_update_rows<T>(W, n, k, (const T*)h->Cpart, parts, n * k, nullptr, (const T*)h->Hm, solve_args(p, false),
-                          (T*)h->Wt, h->ldwt, (T*)h->colsum_part, h->flags, h->ub_blocks_w, st);
-    launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_w, k, h->sums, k, h->world > 1 ? 0 : 2, h->flags, st);
-    h->launches += 2;
-    if (h->world > 1) {
-        // the zero-column test of nmf.py:793 is over ALL rows: all-reduce the shard sums (doubles)
-        NCK(g_nccl.AllReduce(h->sums + k, h->sums + k, (size_t)k, 8, 0, h->comm, st));
-        launch_flag_from_sums(h->sums, k, k, 2, h->flags, st);
-        h->launches += 2;
-    }
+                          (T*)h->Wt, h->ldwt, (T*)h->colsum_part, h->flags, h->ub_blocks_w,
+                          ColsumOut{h->sums, k, h->world > 1 ? 0 : 2, h->counters + 0}, st);
+    h->launches++;
     CKL();
     return 0;
 }
@@ -770,58 +832,57 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
     const int64_t n = h->n, d = h->d;
     T* cg = (T*)h->cg;                 // [d*k | k*k]: X'W partial followed by W'W partial, all-reduced together
     T* G = cg + (size_t)d * k;
+    const bool tc_gram = gram_in_contraction(h);
+    const int psplits = h->math == RRI_MATH_TF32 ? 1 : h->splits_t;
     if (h->world > 1 && h->p2p) {
-        // Fused exchange over NVLink peer memory: this rank's partials [X_i'W_i | W_i'W_i] are produced straight
-        // into its exported slot; after a flag handshake every rank's update kernel reads all slots in place
-        // and adds them in rank order (bit-identical T on all ranks, no separate all-reduce launch).
+        // Exchange over NVLink peer memory fused with the update: this rank's partials [X_i'W_i | W_i'W_i] are
+        // produced straight into its exported slot, then ONE kernel publishes / waits, adds the slices it owns over
+        // all ranks in rank order, updates those rows of T' and stores them into every rank's replicas.
         const unsigned e = ++h->epoch;
         const int b = (int)(e & 1u);
-        char* slot = (char*)h->xbuf + (size_t)(2 * b) * h->xslot_elems * h->es;
-        T* myC = (T*)slot;                                   // partial  [d*k | k*k]
+        T* myC = (T*)((char*)h->xbuf + (size_t)b * h->xslot_elems * h->es);      // partial  [d*k | k*k]
         T* myG = myC + (size_t)d * k;
-        T* redC = (T*)(slot + h->xslot_elems * h->es);       // reduced  [d*k | k*k], filled by the slice owners
-        T* redG = redC + (size_t)d * k;
-        launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, myG, st);
-        h->launches += 2;
-        const int psplits = h->math == RRI_MATH_TF32 ? 1 : h->splits_t;
+        if (!tc_gram) { launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, myG, st); h->launches += 2; }
         T* Cdst = psplits == 1 ? myC : (T*)h->Cpart;
-        if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, Cdst, d, k, n, h->splits_t, st)) return 1;
+        if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, Cdst, d, k, n, h->splits_t, st,
+                           tc_gram ? myG : nullptr)) return 1;
         if (psplits > 1) { launch_reduce_parts<T>((const T*)h->Cpart, psplits, d * k, d * k, myC, st); h->launches++; }
-        unsigned* myflags = (unsigned*)((char*)h->xbuf + 4 * h->xslot_elems * h->es);
-        const int64_t len = (int64_t)h->xslot_elems;
-        int rblocks = (int)((len / (16 / (int64_t)h->es) / h->world + 255) / 256);
-        if (rblocks > 4 * h->sm_count) rblocks = 4 * h->sm_count;
-        if (rblocks < 1) rblocks = 1;
-        peer_signal_kernel<<<1, 1, 0, st>>>(myflags, e);                                   // partial published
-        peer_wait_kernel<<<1, 32, 0, st>>>(h->d_peerFlag, h->world, e, h->p2p_err);
-        peer_reduce_scatter_gather_kernel<T><<<rblocks, 256, 0, st>>>((T* const*)(h->d_peerP + (size_t)b * h->world),
-                                                                       (T* const*)(h->d_peerR + (size_t)b * h->world), h->world, h->rank, len);
-        peer_signal_kernel<<<1, 1, 0, st>>>(myflags + 32, e);                              // my slice stored everywhere
-        peer_wait_kernel<<<1, 32, 0, st>>>(h->d_peerFlag + h->world, h->world, e, h->p2p_err);
-        launch_update_rows<T>((T*)h->Tt, d, k, redC, 1, d * k, nullptr, redG, solve_args(p, true), Tm, d,
-                              (T*)h->colsum_part, h->flags, h->ub_blocks_t, st);
-        launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_t, k, h->sums, 0, 1, h->flags, st);
-        h->launches += 7;
+        const PeerExchange px = peer_args(h, e);
+        const int blocks = peer_update_blocks(px.row_hi - px.row_lo, h->sm_count);
+        if (!launch_peer_update_rows<T>(px, d, k, solve_args(p, true), (T*)h->colsum_part, h->flags, h->sums,
+                                        h->counters + 1, blocks, st))
+            return fail("the fused peer-memory T update does not support k = %d", k);
+        h->launches++;
         CKL();
         return 0;
     }
-    launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, G, st);
-    h->launches += 2;
-    if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
-    const T* C = (const T*)h->Cpart;
-    int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_t;
+    if (!tc_gram) { launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, G, st); h->launches += 2; }
+    // (one rank, TF32: the Gram tile lands right behind the contraction output, as the all-reduce wants it)
+    T* Cout = (h->world > 1 && psplits == 1) ? cg : (T*)h->Cpart;
+    if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, Cout, d, k, n, h->splits_t, st,
+                       tc_gram ? G : nullptr)) return 1;
+    const T* C = Cout;
+    int parts = psplits;
     if (h->world > 1) {
-        launch_reduce_parts<T>(C, parts, d * k, d * k, cg, st);
-        h->launches++;
+        if (psplits > 1) { launch_reduce_parts<T>(C, parts, d * k, d * k, cg, st); h->launches++; }
         if (allreduce(h, cg, (size_t)d * k + (size_t)k * k, st)) return 1;
         C = cg; parts = 1;
     }
     // Tt (d x k) is updated in place; its transpose is written straight into the caller's T (k x d)
     launch_update_rows<T>((T*)h->Tt, d, k, C, parts, d * k, nullptr, G, solve_args(p, true), Tm, d, (T*)h->colsum_part,
-                          h->flags, h->ub_blocks_t, st);
-    launch_colsum_finalize<T>((const T*)h->colsum_part, h->ub_blocks_t, k, h->sums, 0, 1, h->flags, st);
-    h->launches += 2;
+                          h->flags, h->ub_blocks_t, ColsumOut{h->sums, 0, 1, h->counters + 2}, st);
+    h->launches++;
     CKL();
+    return 0;
+}
+
+// once per call on row shards: the zero-column test of nmf.py:793 is over ALL rows
+static int hals_finish_sums(rri_handle_t h, cudaStream_t st)
+{
+    if (h->world <= 1) return 0;
+    NCK(g_nccl.AllReduce(h->sums + h->k, h->sums + h->k, (size_t)h->k, 8, 0, h->comm, st));
+    launch_flag_from_sums(h->sums, h->k, h->k, 2, h->flags, st);
+    h->launches += 2;
     return 0;
 }
 
@@ -848,7 +909,7 @@ static int wrri_T_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p
     if (h->wtc) {
         std::string err;
         parts = h->wtc_groups_t;
-        if (wrri_tc_stats(h->wtc, 0, (const float*)h->X, h->ldx, h->M, h->mk, h->ldm, t, (float*)h->numer_part,
+        if (wrri_tc_stats(h->wtc, 0, (const float*)h->X, h->ldx, h->M, h->mk, h->ldm, t, (const float*)Tm + (int64_t)t * d, (float*)h->numer_part,
                           (float*)h->denom_part, parts, st, err) < 0)
             return fail("tensor-core WRRI T statistics failed: %s", err.c_str());
     } else {
@@ -882,7 +943,7 @@ static int wrri_W_step(rri_handle_t h, T* W, T* Tm, int t, const rri_params_t* p
     if (h->wtc) {
         std::string err;
         parts = h->wtc_groups_w;
-        if (wrri_tc_stats(h->wtc, 1, (const float*)h->X, h->ldx, h->M, h->mk, h->ldm, t, (float*)h->numer_part,
+        if (wrri_tc_stats(h->wtc, 1, (const float*)h->X, h->ldx, h->M, h->mk, h->ldm, t, (const float*)Tm + (int64_t)t * d, (float*)h->numer_part,
                           (float*)h->denom_part, parts, st, err) < 0)
             return fail("tensor-core WRRI W statistics failed: %s", err.c_str());
     } else {
@@ -1103,18 +1164,27 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
         launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
         h->launches++;
         for (int s = 0; s < n_sweeps; ++s)
-            if (hals_W_half<T>(h, W, Tm, p, s == 0, st)) return 1;
-        return 0;
+            if (hals_W_half<T>(h, W, Tm, d, p, s == 0, st)) return 1;
+        return hals_finish_sums(h, st);
     }
     if (h->order == RRI_ORDER_HALS) {
         launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
         launch_transpose<T>(W, n, k, k, (T*)h->Wt, h->ldwt, st);
         h->launches += 2;
+        const bool px = h->world > 1 && h->p2p;
+        // with the peer exchange the current T lives in this rank's replica inside the exchange buffer (the peers
+        // store the rows they update into it); the caller's T is loaded into it here and read back at the end
+        T* Tk = px ? (T*)((char*)h->xbuf + h->x_off_tk) : Tm;
+        const int64_t ldtk = px ? h->ldtk : d;
+        if (px) CK(cudaMemcpy2DAsync(Tk, (size_t)ldtk * sizeof(T), Tm, (size_t)d * sizeof(T), (size_t)d * sizeof(T), (size_t)k,
+                                     cudaMemcpyDeviceToDevice, st));
         for (int s = 0; s < n_sweeps; ++s) {
             if (hals_T_half<T>(h, W, Tm, p, st)) return 1;
-            if (hals_W_half<T>(h, W, Tm, p, true, st)) return 1;
+            if (hals_W_half<T>(h, W, Tk, ldtk, p, true, st)) return 1;
         }
-        return 0;
+        if (px) CK(cudaMemcpy2DAsync(Tm, (size_t)d * sizeof(T), Tk, (size_t)ldtk * sizeof(T), (size_t)d * sizeof(T), (size_t)k,
+                                     cudaMemcpyDeviceToDevice, st));
+        return hals_finish_sums(h, st);
     }
     if (rri_prologue<T>(h, W, 0, p, st)) return 1;
     for (int s = 0; s < n_sweeps; ++s)
@@ -1319,6 +1389,14 @@ extern "C" int rri_cache_trim(int32_t device)
 {
     CK(cudaSetDevice(device));
     cache_trim();
+    // parked exchange buffers: on row shards every rank must trim at the same point (a peer may have this buffer mapped)
+    for (PeerGroup& g : g_groups) {
+        if (!g.used || g.device != device) continue;
+        for (int r = 0; r < 16; ++r)
+            if (g.peer_open[r] && g.peer_base[r]) cudaIpcCloseMemHandle(g.peer_base[r]);
+        cudaFree(g.xbuf);
+        g = PeerGroup();
+    }
     return 0;
 }
 
@@ -1371,6 +1449,23 @@ static int profile_impl(rri_handle_t h, int which, const T* W, const T* Tm, int 
         launch_transpose<T>(W, n, k, k, (T*)h->Wt, h->ldwt, st);
         h->launches++;
     }
+    rri_params_t prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.eps = 1.7763568394002505e-15;
+    const bool halves = which == 3 || which == 4;
+    T* Tk = const_cast<T*>(Tm);
+    int64_t ldtk = d;
+    if (halves) {
+        if (h->mk != MK_NONE || h->order != RRI_ORDER_HALS) return fail("which=3/4 need an unmasked hals-order handle");
+        launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
+        launch_transpose<T>(W, n, k, k, (T*)h->Wt, h->ldwt, st);
+        h->launches += 2;
+        if (h->world > 1 && h->p2p) {
+            Tk = (T*)((char*)h->xbuf + h->x_off_tk); ldtk = h->ldtk;
+            CK(cudaMemcpy2DAsync(Tk, (size_t)ldtk * sizeof(T), Tm, (size_t)d * sizeof(T), (size_t)d * sizeof(T), (size_t)k,
+                                 cudaMemcpyDeviceToDevice, st));
+        }
+    }
     for (int it = -1; it < iters; ++it) {          // one untimed warm-up launch
         if (it == 0) CK(cudaEventRecord(e0, st));
         if (which == 0) {
@@ -1383,6 +1478,11 @@ static int profile_impl(rri_handle_t h, int which, const T* W, const T* Tm, int 
         } else if (which == 2) {
             if (h->mk != MK_NONE || h->order != RRI_ORDER_HALS) return fail("which=2 needs an unmasked hals-order handle");
             if (contraction<T>(h, (const T*)h->Xt, h->ldxt, (const T*)h->Wt, h->ldwt, (T*)h->Cpart, d, k, n, h->splits_t, st)) return 1;
+        } else if (which == 3) {
+            // the whole T half-step (contraction + Gram + exchange + update); collective on row shards
+            if (hals_T_half<T>(h, const_cast<T*>(W), const_cast<T*>(Tm), &prm, st)) return 1;
+        } else if (which == 4) {
+            if (hals_W_half<T>(h, const_cast<T*>(W), Tk, ldtk, &prm, true, st)) return 1;
         } else {
             return fail("bad kernel selector %d", which);
         }

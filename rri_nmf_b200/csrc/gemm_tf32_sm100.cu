@@ -9,8 +9,8 @@
 // it needs (210 TFLOP/s at 6.5 TB/s) is above the FP32 SIMT peak, hence tcgen05.mma kind::tf32.
 //
 // Design
-//   * persistent grid, one CTA per SM, 192 threads = 6 warps: warp 0 TMA producer, warp 1 TMEM owner +
-//     single-thread MMA issuer, warps 2-5 epilogue (one per TMEM lane quarter);
+//   * persistent grid, one CTA per SM, 320 threads = 10 warps: warp 0 TMA producer, warp 1 TMEM owner +
+//     single-thread MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter, half of the columns each);
 //   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, zero fill out of bounds) into
 //     a ring of NS stages: A stage = MT x 128 rows x 32 fp32, B stage = NPAD rows x 32 fp32.  The B tile
 //     (whole factor slab for this K chunk) is shared by the MT row tiles a CTA works on at once, so the
@@ -23,7 +23,12 @@
 //   * stream-K work split: the (row super-tile, K chunk) units are divided evenly over the CTAs, so every
 //     SM streams the same number of bytes whatever M is (no wave quantisation at 157 or 196 tiles).
 //     A CTA whose segment covers a full K range writes C directly; first/last partial segments go to a
-//     per-CTA slot and a small fix-up kernel adds them in CTA order (deterministic, no float atomics).
+//     per-CTA slot, and the LAST contributor to arrive at a split tile (a per-tile counter) adds the slots in
+//     CTA order and writes the tile (deterministic, no float atomics, no second kernel, nobody waits);
+//   * optional auxiliary tile: one more row super-tile whose A operand is a second matrix A2 (in practice the
+//     factor itself, so the tile is the k x k Gram matrix B B' of the same half-step) written to its own
+//     output -- the Gram product of BASELINE.json's kernel group (2) rides on the streaming contraction
+//     instead of costing two more launches per half-step.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -31,6 +36,7 @@
 
 #include "devmem.h"
 #include "gemm_tf32_sm100.h"
+#include "tc_sm100.cuh"
 
 namespace rri {
 
@@ -39,7 +45,6 @@ namespace {
 constexpr int BM = 128;            // rows per UMMA (M of the instruction, cta_group::1)
 constexpr int BK = 32;             // fp32 elements per 128-byte swizzle row
 constexpr int UK = 8;              // K of one tcgen05.mma kind::tf32
-constexpr int THREADS = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int FLUSH = 32;           // K-chunks (x32 floats = 1024 K) accumulated in TMEM before a flush into registers
 constexpr int A_TILE_BYTES = BM * BK * 4;      // 16 KB
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -47,131 +52,22 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 struct GemmParams {
     int64_t M, K;
     int N, NPAD;
-    int64_t n_super, nk, units;    // work: n_super row super-tiles x nk K-chunks
+    int64_t n_super, nk, units;    // work: n_super row super-tiles (the auxiliary one included) x nk K-chunks
+    int64_t n_super_main;          // super-tiles of A; tile index n_super_main (when n_super is one more) reads A2
     float* C;
     int64_t ldc;
+    float* C2;                     // output of the auxiliary tile: rows < M2, leading dimension ldc2
+    int64_t ldc2;
+    int M2;
     float* ws;                     // [grid][2][MT*BM*N] partial slots
+    int* ctr;                      // [n_super] arrival counters of split tiles (all zero between launches)
     int stages;
     int tmem_cols;
     int nbuf;                      // TMEM accumulator buffers (2 when 2*MT*NPAD <= 512 columns)
     int flush;                     // K-chunks per TMEM accumulation run
 };
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) {       // ~4 s
-            if (err) atomicExch(err, code);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ uint64_t policy_evict_first()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t policy_evict_last()
-{
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1, uint64_t pol)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-
-// shared-memory matrix descriptor, K-major, 128-byte swizzle (sm_100 "version 1" format):
-//   [0,14) start address >> 4   [16,30) leading byte offset >> 4 (unused for swizzled K-major; 1)
-//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups   [46,48) version = 1
-//   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = npad
-__device__ __forceinline__ uint32_t make_idesc(int npad)
-{
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
-{
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
+using namespace tc;
 
 // balanced split of `units` over `parts`: first unit of part c
 __host__ __device__ __forceinline__ int64_t part_start(int64_t units, int parts, int64_t c)
@@ -189,9 +85,12 @@ __host__ __device__ __forceinline__ int64_t part_of(int64_t units, int parts, in
 // ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
-template <int MT, int NPAD>
-__global__ void __launch_bounds__(THREADS, 1)
-tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p, int* err)
+// EWQ = epilogue warps per TMEM lane quarter (each takes NPAD/EWQ accumulator columns of every tile): 2 for
+// k <= 64, 4 for wider ranks so that a thread never holds more than 64 accumulators
+template <int MT, int NPAD, int EWQ>
+__global__ void __launch_bounds__(64 + 128 * EWQ, 1)
+tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, GemmParams p, int* err)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [A stages][B stages][barriers][tmem ptr]
@@ -205,6 +104,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = empty + p.stages;       // [2] accumulator buffer filled
     uint64_t* tempty = tfull + 2;             // [2] accumulator buffer drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    int* fix_info = reinterpret_cast<int*>(tmem_slot + 1);   // [3] arrival order / first / last contributor of a split tile
+    const float** fix_src = reinterpret_cast<const float**>(full + 64);    // [<= gridDim.x] slot of every contributor
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t u_begin = part_start(p.units, gridDim.x, blockIdx.x);
@@ -213,8 +114,9 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (p.n_super > p.n_super_main) prefetch_tmap(&tmA2);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * EWQ); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -237,7 +139,11 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int64_t kc = kc0; kc < kc0 + len; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1, err, 1);
                     mbar_expect_tx(&full[stage], (uint32_t)(a_stage + b_stage));
-                    tma_load_2d(&tmA, smA + (size_t)stage * a_stage, &full[stage], (int)(kc * BK), (int)(s * MT * BM), polA);
+                    if (s < p.n_super_main)
+                        tma_load_2d(&tmA, smA + (size_t)stage * a_stage, &full[stage], (int)(kc * BK), (int)(s * MT * BM), polA);
+                    else        // auxiliary tile: rows of A2 (rows beyond M2 are zero-filled by TMA)
+                        tma_load_2d(&tmA2, smA + (size_t)stage * a_stage, &full[stage], (int)(kc * BK),
+                                    (int)((s - p.n_super_main) * MT * BM), polB);
                     tma_load_2d(&tmB, smB + (size_t)stage * b_stage, &full[stage], (int)(kc * BK), 0, polB);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -247,7 +153,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ===================================== MMA issuer =======================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(NPAD);
+            const uint32_t idesc = make_idesc_tf32(BM, NPAD);
             int stage = 0; uint32_t phase = 0;
             uint32_t run = 0;                                     // accumulation runs issued so far
             for (int64_t u = u_begin; u < u_end;) {
@@ -284,10 +190,11 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ===================================== epilogue =========================================
-        // 8 warps: warp pair (q, h) owns TMEM lanes [32q, 32q+32) and columns [h*NPAD/2, (h+1)*NPAD/2) of every tile
+        // 4*EWQ warps: warp (q, h) owns TMEM lanes [32q, 32q+32) and columns [h*NPAD/EWQ, (h+1)*NPAD/EWQ) of every tile
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;
-        constexpr int HC = NPAD / 2;                              // columns per thread and tile
+        constexpr int HC = NPAD / EWQ;                            // columns per thread and tile
+        constexpr int EPI_THREADS = 128 * EWQ;
         constexpr int NACC = MT * HC;
         float acc[NACC];
         uint32_t run = 0;
@@ -318,26 +225,93 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[b]);
             }
-            // ---- the segment is complete: write it out (full K range -> C, otherwise -> this CTA's partial slot)
-            float* dst; int64_t ld; int64_t row_base; int64_t row_limit;
-            if (complete) { dst = p.C; ld = p.ldc; row_base = s * MT * BM; row_limit = p.M; }
-            else {
+            // ---- the segment is done: a full K range goes straight to its output tile; a partial one goes to this
+            // CTA's slot, and whichever contributor arrives last at the tile adds all slots in CTA order
+            const bool aux = s >= p.n_super_main;
+            float* out = aux ? p.C2 : p.C;
+            const int64_t out_ld = aux ? p.ldc2 : p.ldc;
+            const int64_t out_row0 = (aux ? s - p.n_super_main : s) * MT * BM;
+            const int64_t out_rows = aux ? (int64_t)p.M2 : p.M;
+            int c_lo = 0, c_hi = 0;
+            if (!complete) {
                 const int slot = (u == u_begin) ? 0 : 1;
-                dst = p.ws + ((int64_t)blockIdx.x * 2 + slot) * slot_elems; ld = p.N; row_base = 0; row_limit = MT * BM;
-            }
+                float* dst = p.ws + ((int64_t)blockIdx.x * 2 + slot) * slot_elems;
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int64_t row = row_base + mt * BM + q * 32 + lane;
-                if (row < row_limit) {
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int row = mt * BM + q * 32 + lane;
 #pragma unroll
                     for (int c0 = 0; c0 < HC; c0 += 4) {
                         const int col = h * HC + c0;
-                        float* o = dst + row * ld + col;
-                        if ((col + 4 <= p.N) && ((ld & 3) == 0)) {
-                            *reinterpret_cast<float4*>(o) = make_float4(acc[mt * HC + c0], acc[mt * HC + c0 + 1], acc[mt * HC + c0 + 2], acc[mt * HC + c0 + 3]);
+                        float* o = dst + (int64_t)row * p.N + col;
+                        if ((col + 4 <= p.N) && ((p.N & 3) == 0)) {
+                            __stcg(reinterpret_cast<float4*>(o), make_float4(acc[mt * HC + c0], acc[mt * HC + c0 + 1], acc[mt * HC + c0 + 2], acc[mt * HC + c0 + 3]));
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) if (col + j < p.N) o[j] = acc[mt * HC + c0 + j];
+                            for (int j = 0; j < 4; ++j) if (col + j < p.N) __stcg(o + j, acc[mt * HC + c0 + j]);
+                        }
+                    }
+                }
+                __threadfence();                                              // slot visible before the arrival below
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // the epilogue warps
+                if (threadIdx.x == 64) {
+                    const int64_t u0 = s * p.nk;
+                    const int lo = (int)part_of(p.units, gridDim.x, u0), hi = (int)part_of(p.units, gridDim.x, u0 + p.nk - 1);
+                    fix_info[0] = atomicAdd(p.ctr + s, 1);
+                    fix_info[1] = lo; fix_info[2] = hi;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                c_lo = fix_info[1]; c_hi = fix_info[2];
+                if (fix_info[0] == c_hi - c_lo) {                             // every other contributor has arrived
+                    __threadfence();
+                    // flat, coalesced sum of all contributors' slots (own one included) straight into the output tile
+                    const int et = (int)threadIdx.x - 64;
+                    const int64_t u0 = s * p.nk;
+                    const int ncontrib = c_hi - c_lo + 1;
+                    for (int i = et; i < ncontrib; i += EPI_THREADS) {
+                        const int64_t cta = c_lo + i;
+                        const int cslot = part_start(p.units, gridDim.x, cta) >= u0 ? 0 : 1;
+                        fix_src[i] = p.ws + (cta * 2 + cslot) * slot_elems;
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+                    const int64_t rows_left = out_rows - out_row0;
+                    const int nvalid = (int)(rows_left < (int64_t)MT * BM ? rows_left : (int64_t)MT * BM) * p.N;
+                    float* tile = out + out_row0 * out_ld;
+                    if (out_ld == p.N && (p.N & 3) == 0) {
+                        for (int e = et * 4; e < nvalid; e += EPI_THREADS * 4) {
+                            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int i = 0; i < ncontrib; ++i) {
+                                const float4 v = __ldcg(reinterpret_cast<const float4*>(fix_src[i] + e));
+                                a4.x += v.x; a4.y += v.y; a4.z += v.z; a4.w += v.w;
+                            }
+                            *reinterpret_cast<float4*>(tile + e) = a4;
+                        }
+                    } else {
+                        for (int e = et; e < nvalid; e += EPI_THREADS) {
+                            float a1 = 0.f;
+                            for (int i = 0; i < ncontrib; ++i) a1 += __ldcg(fix_src[i] + e);
+                            const int r = e / p.N, c = e - r * p.N;
+                            tile[(int64_t)r * out_ld + c] = a1;
+                        }
+                    }
+                    if (threadIdx.x == 64) p.ctr[s] = 0;                      // ready for the next launch
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // fix_info / fix_src are reused by the next segment
+            }
+            if (complete) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int64_t row = out_row0 + mt * BM + q * 32 + lane;
+                    if (row < out_rows) {
+#pragma unroll
+                        for (int c0 = 0; c0 < HC; c0 += 4) {
+                            const int col = h * HC + c0;
+                            float* o = out + row * out_ld + col;
+                            if ((col + 4 <= p.N) && ((out_ld & 3) == 0)) {
+                                *reinterpret_cast<float4*>(o) = make_float4(acc[mt * HC + c0], acc[mt * HC + c0 + 1], acc[mt * HC + c0 + 2], acc[mt * HC + c0 + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) if (col + j < p.N) o[j] = acc[mt * HC + c0 + j];
+                            }
                         }
                     }
                 }
@@ -350,53 +324,6 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
-    }
-}
-
-// adds the partial segments of every split row super-tile in CTA order.  A stream-K split over G CTAs
-// cuts at most G-1 super-tiles, so the grid is one block per CTA boundary: boundary b (between CTA b and
-// b+1) owns the super-tile that contains unit part_start(b+1) -- if that unit is not a tile start and no
-// earlier boundary falls into the same tile.
-template <int MT>
-__global__ void __launch_bounds__(256)
-tf32_gemm_fixup_kernel(GemmParams p, int grid_main)
-{
-    const int64_t ub = part_start(p.units, grid_main, (int64_t)blockIdx.x + 1);   // first unit of CTA b+1
-    if (ub % p.nk == 0) return;                                   // the cut falls on a tile boundary
-    const int64_t s = ub / p.nk;
-    const int64_t u0 = s * p.nk, u1 = u0 + p.nk;
-    const int64_t c_lo = part_of(p.units, grid_main, u0), c_hi = part_of(p.units, grid_main, u1 - 1);
-    if (c_lo != (int64_t)blockIdx.x) return;                      // an earlier boundary owns this tile
-    const int slot_elems = MT * BM * p.N;
-    const int64_t row0 = s * MT * BM;
-    const int rows = (int)((p.M - row0) < (int64_t)MT * BM ? (p.M - row0) : (int64_t)MT * BM);
-    const int nvalid = rows * p.N;
-    // slot base of every contributing CTA, computed once (64-bit divisions are slow)
-    __shared__ const float* src[160];
-    const int ncontrib = (int)(c_hi - c_lo + 1);
-    for (int i = threadIdx.x; i < ncontrib; i += blockDim.x) {
-        const int64_t cta = c_lo + i;
-        const int slot = part_start(p.units, grid_main, cta) >= u0 ? 0 : 1;
-        src[i] = p.ws + (cta * 2 + slot) * (int64_t)slot_elems;
-    }
-    __syncthreads();
-    float* dst = p.C + row0 * p.ldc;
-    if (p.ldc == p.N && (nvalid & 3) == 0) {
-        for (int e = threadIdx.x * 4; e < nvalid; e += blockDim.x * 4) {
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = 0; i < ncontrib; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(src[i] + e);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            *reinterpret_cast<float4*>(dst + e) = acc;
-        }
-    } else {
-        for (int e = threadIdx.x; e < nvalid; e += blockDim.x) {
-            float acc = 0.f;
-            for (int i = 0; i < ncontrib; ++i) acc += src[i][e];
-            const int r = e / p.N, c = e - r * p.N;
-            dst[(int64_t)r * p.ldc + c] = acc;
-        }
     }
 }
 
@@ -416,6 +343,8 @@ struct Tf32Gemm {
     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
     int force_mt = 0;
     int flush = FLUSH;
+    int* ctr = nullptr;
+    size_t ctr_len = 0;
 };
 
 Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
@@ -456,6 +385,7 @@ void tf32_gemm_destroy(Tf32Gemm* g)
     if (!g) return;
     if (g->ws) cached_free(g->ws);
     if (g->err) cached_free(g->err);
+    if (g->ctr) cached_free(g->ctr);
     delete g;
 }
 
@@ -483,10 +413,11 @@ static bool encode_2d(Tf32Gemm* g, CUtensorMap* tm, const float* base, int64_t r
 }
 
 template <int MT, int NPAD>
-static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, cudaStream_t st, std::string& err)
+static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, GemmParams p,
+                   cudaStream_t st, std::string& err)
 {
     const int a_stage = MT * A_TILE_BYTES, b_stage = NPAD * BK * 4;
-    const int bar_bytes = 1024;
+    const int bar_bytes = 4096;       // mbarriers, TMEM slot, fix-up scratch (one slot pointer per CTA of the grid)
     int stages = (SMEM_LIMIT - 1024 /*alignment slack*/ - bar_bytes) / (a_stage + b_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) { err = "not enough shared memory for two pipeline stages"; return -1; }
@@ -498,20 +429,21 @@ static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     p.tmem_cols = cols;
     p.flush = g->flush > 0 ? g->flush : (1 << 30);
     int64_t grid = p.units < g->sm_count ? p.units : g->sm_count;
-    auto kern = tf32_gemm_kernel<MT, NPAD>;
+    constexpr int EWQ = NPAD >= 128 ? 4 : 2;
+    auto kern = tf32_gemm_kernel<MT, NPAD, EWQ>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         err = "cudaFuncSetAttribute(max dynamic smem) failed";
         return -1;
     }
-    kern<<<(unsigned)grid, THREADS, smem, st>>>(tmA, tmB, p, g->err);
-    if (grid > 1) tf32_gemm_fixup_kernel<MT><<<(unsigned)(grid - 1), 256, 0, st>>>(p, (int)grid);
+    kern<<<(unsigned)grid, 64 + 128 * EWQ, smem, st>>>(tmA, tmB, tmA2, p, g->err);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = cudaGetErrorString(e); return -1; }
-    return 2;
+    return 1;
 }
 
 int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                  int64_t M, int N, int64_t K, cudaStream_t st, std::string& err)
+                  int64_t M, int N, int64_t K, cudaStream_t st, std::string& err, const float* A2, int64_t lda2, int M2,
+                  float* C2, int64_t ldc2)
 {
     if (!g) { err = "null contraction handle"; return -1; }
     if (N < 1 || N > 256) { err = "N must be in [1,256]"; return -1; }
@@ -520,18 +452,33 @@ int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int6
     int mt = (M > BM) ? 2 : 1;
     if (npad == 256) mt = 1;                     // 128 accumulator registers per epilogue thread at most
     if (g->force_mt == 1 || (g->force_mt == 2 && npad < 256)) mt = g->force_mt;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmA2;
     if (!encode_2d(g, &tmA, A, M, K, lda, mt * BM, err)) return -1;
     if (!encode_2d(g, &tmB, B, N, K, ldb, npad, err)) return -1;
+    const bool aux = A2 != nullptr && M2 > 0 && C2 != nullptr;
+    if (aux) { if (!encode_2d(g, &tmA2, A2, M2, K, lda2, mt * BM, err)) return -1; }
+    else tmA2 = tmA;
     GemmParams p;
     p.M = M; p.K = K; p.N = N; p.NPAD = npad;
-    p.n_super = (M + (int64_t)mt * BM - 1) / ((int64_t)mt * BM);
+    p.n_super_main = (M + (int64_t)mt * BM - 1) / ((int64_t)mt * BM);
+    p.n_super = p.n_super_main + (aux ? (M2 + mt * BM - 1) / (mt * BM) : 0);
     p.nk = (K + BK - 1) / BK;
     p.units = p.n_super * p.nk;
     p.C = C; p.ldc = ldc; p.ws = g->ws;
+    p.C2 = aux ? C2 : C; p.ldc2 = aux ? ldc2 : ldc; p.M2 = aux ? M2 : 0;
+    if (p.n_super > (int64_t)g->ctr_len) {
+        // arrival counters of split tiles: zero between launches (the last contributor resets its tile's counter)
+        if (g->ctr) cached_free(g->ctr);
+        g->ctr = nullptr; g->ctr_len = 0;
+        const size_t len = (size_t)(p.n_super + 1023) / 1024 * 1024;
+        if (cached_malloc((void**)&g->ctr, len * sizeof(int)) != cudaSuccess) { err = "tile counter allocation failed"; return -1; }
+        if (cudaMemsetAsync(g->ctr, 0, len * sizeof(int), st) != cudaSuccess) { err = "tile counter reset failed"; return -1; }
+        g->ctr_len = len;
+    }
+    p.ctr = g->ctr;
     p.stages = 0; p.tmem_cols = 0;
     p.nbuf = 1; p.flush = 0;
-#define RRI_GEMM_CASE(MTv, NP) if (mt == MTv && npad == NP) return run_cfg<MTv, NP>(g, tmA, tmB, p, st, err)
+#define RRI_GEMM_CASE(MTv, NP) if (mt == MTv && npad == NP) return run_cfg<MTv, NP>(g, tmA, tmB, tmA2, p, st, err)
     RRI_GEMM_CASE(2, 32); RRI_GEMM_CASE(2, 64); RRI_GEMM_CASE(2, 128);
     RRI_GEMM_CASE(1, 32); RRI_GEMM_CASE(1, 64); RRI_GEMM_CASE(1, 128); RRI_GEMM_CASE(1, 256);
 #undef RRI_GEMM_CASE

@@ -108,6 +108,37 @@ void launch_simt_gemm_nt(const T* A, int64_t lda, const T* B, int64_t ldb, T* Cp
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused finalisation of the per-block column sums: the LAST block to finish (an arrival counter, nobody waits) adds
+// the block partials in the fixed order of the former colsum_finalize_kernel (a warp per column, lanes stride over
+// the blocks, shuffle tree) and sets the zero-topic / non-finite flags -- one launch less per half-step
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void colsum_tail(const T* __restrict__ colsum_part, int k, double* __restrict__ sums, int off,
+                                            int zero_flag, int* __restrict__ flags, unsigned* __restrict__ counter)
+{
+    __shared__ unsigned s_arrival;
+    __threadfence();                                   // this block's partial sums before its arrival
+    __syncthreads();
+    if (threadIdx.x == 0) s_arrival = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (s_arrival != gridDim.x - 1) return;
+    __threadfence();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int col = warp; col < k; col += nw) {
+        T s = T(0);
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(colsum_part + (int64_t)b * k + col);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const double v = (double)s;
+            sums[off + col] = v;
+            if (zero_flag && !(v > 1e-10)) atomicOr(flags, zero_flag);
+            if (!isfinite(v)) atomicOr(flags, 8);
+        }
+    }
+    if (threadIdx.x == 0) *counter = 0u;              // ready for the next launch
+}
+
+// ------------------------------------------------------------------------------------------------
 // row update: warp per row, lanes own coordinates t' = lane + 32 l
 // ------------------------------------------------------------------------------------------------
 constexpr int U_THREADS = 256, U_NW = U_THREADS / WARP, U_GROUP = 32;   // rows per block iteration
@@ -124,7 +155,8 @@ __global__ void __launch_bounds__(U_THREADS)
 update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cpart, int parts,
                    int64_t part_stride, const T* const* __restrict__ srcs, const T* __restrict__ S,
                    T reg_l1, T reg_l2, T eps, T ub, int has_ub,
-                   T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags)
+                   T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags,
+                   double* __restrict__ sums, int sums_off, int zero_flag, unsigned* __restrict__ counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* ftile = reinterpret_cast<T*>(smem_raw);                 // [k][U_GROUP+1]
@@ -231,12 +263,13 @@ update_rows_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cp
         for (int w = 0; w < U_NW; ++w) s += csm[w * k + tp];
         colsum_part[(int64_t)blockIdx.x * k + tp] = s;
     }
+    if (sums) colsum_tail<T>(colsum_part, k, sums, sums_off, zero_flag, flags, counter);
 }
 
 template <typename T, int KL>
 static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
                                   const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
-                                  int* flags, int blocks, cudaStream_t st)
+                                  int* flags, int blocks, const ColsumOut& co, cudaStream_t st)
 {
     size_t base = sizeof(T) * ((size_t)k * (U_GROUP + 1) + (size_t)U_NW * k);
     size_t with_s = base + sizeof(T) * (size_t)k * k;
@@ -245,13 +278,13 @@ static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int pa
         if (with_s > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_s);
         kern<<<blocks, U_THREADS, with_s, st>>>(F, m, k, Cpart, parts, part_stride, srcs, S, (T)a.reg_l1,
                                                  (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft,
-                                                 colsum_part, flags);
+                                                 colsum_part, flags, co.sums, co.off, co.zero_flag, co.counter);
     } else {
         auto kern = update_rows_kernel<T, KL, false>;
         if (base > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)base);
         kern<<<blocks, U_THREADS, base, st>>>(F, m, k, Cpart, parts, part_stride, srcs, S, (T)a.reg_l1,
                                                (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft,
-                                               colsum_part, flags);
+                                               colsum_part, flags, co.sums, co.off, co.zero_flag, co.counter);
     }
 }
 
@@ -265,15 +298,55 @@ static void launch_update_rows_kl(T* F, int64_t m, int k, const T* Cpart, int pa
 // ------------------------------------------------------------------------------------------------
 constexpr int TPR_ROWS = 128;       // rows (= threads) per block
 
+// The k sequential scalar solves of one row (thread `tid` owns row `tid` of the staged tiles): topics in groups of
+// 8, t = 8c + u with u unrolled, so the register holding f[t] can only be one of the 8 entries f[u], f[u+8], ... --
+// 8 selects per step instead of KM.  ctile/ftile: [TPR_ROWS][KM+1] staged contraction / factor rows; Ss: [KM][KM].
+template <typename T, int KM>
+__device__ __forceinline__ void tpr_solve_row(const T* __restrict__ Ss, const T* __restrict__ ctile, T* __restrict__ ftile,
+                                              int tid, int k, T reg_l1, T reg_l2, T eps, T ub, bool has_ub, bool& unb)
+{
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    constexpr int LD = KM + 1;
+    T f[KM];
+#pragma unroll
+    for (int j = 0; j < KM; ++j) f[j] = (j < k) ? ftile[tid * LD + j] : T(0);
+#pragma unroll 1
+    for (int c = 0; c < (k + 7) / 8; ++c) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = 8 * c + u;
+            if (t < k) {
+                const V* srow = reinterpret_cast<const V*>(Ss + t * KM);
+                T acc[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+                for (int jv = 0; jv < KM / VN; ++jv) {
+                    T sv[VN];
+                    unpack(srow[jv], sv);
+#pragma unroll
+                    for (int v = 0; v < VN; ++v) acc[(jv * VN + v) & 3] = fma(f[jv * VN + v], sv[v], acc[(jv * VN + v) & 3]);
+                }
+                const T stt = Ss[t * KM + t];
+                const T ft = ftile[tid * LD + t];
+                // sum over j != t: remove the own term from the full dot product
+                const T dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
+                const T x = solve_scalar_c<T>(ctile[tid * LD + t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub, unb);
+                ftile[tid * LD + t] = x;
+#pragma unroll
+                for (int jj = 0; jj < KM / 8; ++jj) f[8 * jj + u] = (jj == c) ? x : f[8 * jj + u];
+            }
+        }
+    }
+}
+
 template <typename T, int KM>
 __global__ void __launch_bounds__(TPR_ROWS)
 update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ Cpart, int parts,
                        int64_t part_stride, const T* const* __restrict__ srcs, const T* __restrict__ S,
                        T reg_l1, T reg_l2, T eps, T ub, int has_ub,
-                       T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags)
+                       T* __restrict__ Ft, int64_t ldft, T* __restrict__ colsum_part, int* __restrict__ flags,
+                       double* __restrict__ sums, int sums_off, int zero_flag, unsigned* __restrict__ counter)
 {
-    using V = typename Vec<T>::type;
-    constexpr int VN = Vec<T>::N;
     constexpr int LD = KM + 1;                              // padded row stride of the tiles
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* Ss = reinterpret_cast<T*>(smem_raw);                 // [KM][KM], zero padded, 16-byte aligned rows
@@ -332,39 +405,7 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
             }
         }
         __syncthreads();
-        T f[KM];
-#pragma unroll
-        for (int j = 0; j < KM; ++j) f[j] = (j < k && tid < nrow) ? ftile[tid * LD + j] : T(0);
-        if (tid < nrow) {
-            // topics in groups of 8: t = 8c + u with u unrolled, so the register holding f[t] can only be one
-            // of the 8 entries f[u], f[u+8], ... -- 8 selects per step instead of KM
-#pragma unroll 1
-            for (int c = 0; c < (k + 7) / 8; ++c) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int t = 8 * c + u;
-                    if (t < k) {
-                        const V* srow = reinterpret_cast<const V*>(Ss + t * KM);
-                        T acc[4] = {T(0), T(0), T(0), T(0)};
-#pragma unroll
-                        for (int jv = 0; jv < KM / VN; ++jv) {
-                            T sv[VN];
-                            unpack(srow[jv], sv);
-#pragma unroll
-                            for (int v = 0; v < VN; ++v) acc[(jv * VN + v) & 3] = fma(f[jv * VN + v], sv[v], acc[(jv * VN + v) & 3]);
-                        }
-                        const T stt = Ss[t * KM + t];
-                        const T ft = ftile[tid * LD + t];
-                        // sum over j != t: remove the own term from the full dot product
-                        const T dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
-                        const T x = solve_scalar_c<T>(ctile[tid * LD + t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
-                        ftile[tid * LD + t] = x;
-#pragma unroll
-                        for (int jj = 0; jj < KM / 8; ++jj) f[8 * jj + u] = (jj == c) ? x : f[8 * jj + u];
-                    }
-                }
-            }
-        }
+        if (tid < nrow) tpr_solve_row<T, KM>(Ss, ctile, ftile, tid, k, reg_l1, reg_l2, eps, ub, has_ub != 0, unb);
         __syncthreads();
         {   // write back: F (row-major, coalesced), column sums, transposed copy
             const int tot = nrow * k;
@@ -376,7 +417,6 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
                 rr += dr; cc += dc;
                 if (cc >= k) { cc -= k; ++rr; }
             }
-            // column sums: TPR_ROWS/KM-way split of the rows per column when the block has spare threads
             if (tid < k) {
                 T cs = T(0);
 #pragma unroll 8
@@ -393,38 +433,278 @@ update_rows_tpr_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
     }
     if (unb) atomicOr(flags, 4);
     if (tid < k) colsum_part[(int64_t)blockIdx.x * k + tid] = csum;
+    if (sums) colsum_tail<T>(colsum_part, k, sums, sums_off, zero_flag, flags, counter);
 }
 
 template <typename T, int KM>
 static void launch_update_rows_tpr(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
                                    const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft, T* colsum_part,
-                                   int* flags, int blocks, cudaStream_t st)
+                                   int* flags, int blocks, const ColsumOut& co, cudaStream_t st)
 {
     const size_t smem = sizeof(T) * ((size_t)KM * KM + 2 * (size_t)TPR_ROWS * (KM + 1));
     auto kern = update_rows_tpr_kernel<T, KM>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<blocks, TPR_ROWS, smem, st>>>(F, m, k, Cpart, parts, part_stride, srcs, S, (T)a.reg_l1, (T)a.reg_l2,
-                                        (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft, colsum_part, flags);
+                                        (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft, colsum_part, flags, co.sums, co.off,
+                                        co.zero_flag, co.counter);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU T half-step: exchange over NVLink peer memory FUSED with the rank-one updates (one launch).
+//
+// Every rank r holds, in an exchange buffer that all ranks have mapped, its partial statistic of this sweep
+// [X_r'W_r (d x k) | W_r'W_r (k x k)] (nmf.py:680-686, batched over topics), a replica of T' (d x k, the factor
+// rows this kernel updates) and of T (k x ldtk, the operand of the next W half-step).  Rank r owns the rows
+// [row_lo, row_hi) of T':
+//   1. publish "my partial is complete" to every peer (flag1, release at system scope) and wait for all peers';
+//   2. add the k x k Gram partials and, per 128-row block, the contraction rows of all ranks in rank order
+//      (in-place NVLink reads: the reduce-scatter half of an all-reduce, never materialised);
+//   3. run the k sequential solves of those rows (nmf.py:437-447 with the Gram form of :672-676);
+//   4. store the new rows into EVERY rank's T' and T replicas (NVLink writes: the all-gather half) and the slice's
+//      column sums into every rank's tsum table;
+//   5. the last block to finish publishes flag2 to every peer, waits for all peers' flag2 -- after which this rank's
+//      replicas are complete -- and finalises sum(T[t,:]) (nmf.py:757) from the tsum table.
+// Each T entry is computed by exactly one rank from sums taken in a fixed order: the replicas are bit-identical.
+// The work of the T update is divided by the number of ranks instead of being repeated on each of them.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void peer_flag_store(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned peer_flag_load(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// threads r < world wait until peer r has published `epoch` in this rank's flag array
+__device__ __forceinline__ void peer_wait_all(const unsigned* flags_local, int world, unsigned epoch, int* err)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        const long long t0 = clock64();
+        while ((int)(peer_flag_load(flags_local + 32 * r) - epoch) < 0) {
+            if (clock64() - t0 > 200000000000LL) {     // ~100 s: a lost peer must not hang the GPU for ever
+                atomicExch(err, 1 + r);
+                __trap();
+            }
+            __nanosleep(100);
+        }
+    }
+}
+
+template <typename T, int KM>
+__global__ void __launch_bounds__(TPR_ROWS)
+peer_update_rows_kernel(PeerExchange px, int64_t d, int k, T reg_l1, T reg_l2, T eps, T ub, int has_ub,
+                        T* __restrict__ colsum_part, int* __restrict__ flags, double* __restrict__ sums,
+                        unsigned* __restrict__ counter)
+{
+    constexpr int LD = KM + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Ss = reinterpret_cast<T*>(smem_raw);
+    T* ctile = Ss + KM * KM;
+    T* ftile = ctile + TPR_ROWS * LD;
+    __shared__ unsigned s_arrival;
+    const int tid = threadIdx.x;
+    const int world = px.world, rank = px.rank;
+    // ---- 1. publish / wait
+    if (blockIdx.x == 0 && tid < world) {
+        __threadfence_system();
+        peer_flag_store(px.flag1[tid] + 32 * rank, px.epoch);
+    }
+    peer_wait_all(px.flag1[rank], world, px.epoch, px.err);
+    __syncthreads();
+    // ---- 2a. Gram: sum of the ranks' partials in rank order.  A remote load takes ~2 us, so the loads of ALL ranks for a
+    // batch of elements are issued before the first add (a dependent chain per element would cost world x latency)
+    const int64_t goff = d * (int64_t)k;
+    {
+        constexpr int GB = 4;                                   // elements per thread and batch
+        for (int e0 = tid; e0 < k * k; e0 += GB * TPR_ROWS) {
+            T v[16][GB];
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                if (r < world) {
+                    const T* Gp = reinterpret_cast<const T*>(px.part[r]) + goff;
+#pragma unroll
+                    for (int u = 0; u < GB; ++u) {
+                        const int e = e0 + u * TPR_ROWS;
+                        v[r][u] = e < k * k ? __ldcg(Gp + e) : T(0);
+                    }
+                }
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                const int e = e0 + u * TPR_ROWS;
+                if (e < k * k) {
+                    T acc = T(0);
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        if (r < world) acc += v[r][u];
+                    Ss[(e / k) * KM + (e % k)] = acc;
+                }
+            }
+        }
+        if (k < KM)                                             // zero padding of the KM x KM tile
+            for (int e = tid; e < KM * KM; e += TPR_ROWS)
+                if (e / KM >= k || e % KM >= k) Ss[e] = T(0);
+    }
+    T csum = T(0);
+    bool unb = false;
+    __syncthreads();
+    const int64_t m = px.row_hi - px.row_lo;
+    const int64_t ngroups = (m + TPR_ROWS - 1) / TPR_ROWS;
+    T* Floc = reinterpret_cast<T*>(px.Tt[rank]);
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t i0 = px.row_lo + g * TPR_ROWS;
+        const int nrow = (int)((px.row_hi - i0) < TPR_ROWS ? (px.row_hi - i0) : TPR_ROWS);
+        {   // ---- 2b. staging: contraction rows summed over the ranks (in place, over NVLink), own factor rows; the
+            // loads of all ranks for a batch of elements are in flight together (see 2a)
+            const int tot = nrow * k;
+            int rr = tid / k, cc = tid - rr * k;
+            const int dr = TPR_ROWS / k, dc = TPR_ROWS - dr * k;
+            const T* Frow = Floc + i0 * k;
+            constexpr int UB = 4;
+            for (int e0 = tid; e0 < tot; e0 += UB * TPR_ROWS) {
+                T cv[16][UB], fv[UB];
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    if (r < world) {
+                        const T* Cp = reinterpret_cast<const T*>(px.part[r]) + i0 * k;
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+                            const int e = e0 + u * TPR_ROWS;
+                            cv[r][u] = e < tot ? __ldcg(Cp + e) : T(0);
+                        }
+                    }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int e = e0 + u * TPR_ROWS;
+                    fv[u] = e < tot ? Frow[e] : T(0);
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int e = e0 + u * TPR_ROWS;
+                    if (e < tot) {
+                        T acc = T(0);
+#pragma unroll
+                        for (int r = 0; r < 16; ++r)
+                            if (r < world) acc += cv[r][u];
+                        ctile[rr * LD + cc] = acc;
+                        ftile[rr * LD + cc] = fv[u];
+                    }
+                    rr += dr; cc += dc;
+                    if (cc >= k) { cc -= k; ++rr; }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 3. the k sequential solves
+        if (tid < nrow) tpr_solve_row<T, KM>(Ss, ctile, ftile, tid, k, reg_l1, reg_l2, eps, ub, has_ub != 0, unb);
+        __syncthreads();
+        {   // ---- 4. fan-out: the new rows into every rank's T' (row-major) and T (transposed) replicas
+            const int tot = nrow * k;
+            for (int r = 0; r < world; ++r) {
+                const int pr = (rank + r) % world;                     // start with the own copy, spread the peers
+                T* Frow = reinterpret_cast<T*>(px.Tt[pr]) + i0 * k;
+                int rr = tid / k, cc = tid - rr * k;
+                const int dr = TPR_ROWS / k, dc = TPR_ROWS - dr * k;
+                for (int e = tid; e < tot; e += TPR_ROWS) {
+                    Frow[e] = ftile[rr * LD + cc];
+                    rr += dr; cc += dc;
+                    if (cc >= k) { cc -= k; ++rr; }
+                }
+                T* Ft = reinterpret_cast<T*>(px.Tk[pr]);
+                if (tid < nrow)
+                    for (int tp = 0; tp < k; ++tp) Ft[(int64_t)tp * px.ldtk + i0 + tid] = ftile[tid * LD + tp];
+            }
+            if (tid < k) {
+                T cs = T(0);
+#pragma unroll 8
+                for (int ii = 0; ii < nrow; ++ii) cs += ftile[ii * LD + tid];
+                csum += cs;
+            }
+        }
+        __syncthreads();
+    }
+    if (unb) atomicOr(flags, 4);
+    if (tid < k) colsum_part[(int64_t)blockIdx.x * k + tid] = csum;
+    // ---- 5. last block: slice sums to every rank, flag2, wait for the peers, finalise sum(T[t,:])
+    __threadfence_system();                            // this block's stores (local and remote) before its arrival
+    __syncthreads();
+    if (tid == 0) s_arrival = atomicAdd(counter, 1u);
+    __syncthreads();
+    if (s_arrival != gridDim.x - 1) return;
+    __threadfence();
+    if (tid < k) {
+        T s = T(0);
+        for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(colsum_part + (int64_t)b * k + tid);
+        for (int r = 0; r < world; ++r) reinterpret_cast<T*>(px.tsum[r])[rank * k + tid] = s;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        __threadfence_system();
+        peer_flag_store(px.flag2[tid] + 32 * rank, px.epoch);
+    }
+    peer_wait_all(px.flag2[rank], world, px.epoch, px.err);
+    __syncthreads();
+    if (tid < k) {
+        const T* ts = reinterpret_cast<const T*>(px.tsum[rank]);
+        T s = T(0);
+        for (int r = 0; r < world; ++r) s += __ldcg(ts + r * k + tid);
+        const double v = (double)s;
+        sums[tid] = v;
+        if (!(v > 1e-10)) atomicOr(flags, 1);
+        if (!isfinite(v)) atomicOr(flags, 8);
+    }
+    if (tid == 0) *counter = 0u;
+}
+
+int peer_update_blocks(int64_t rows, int sm_count)
+{
+    int64_t b = (rows + TPR_ROWS - 1) / TPR_ROWS;
+    if (b > 2 * sm_count) b = 2 * sm_count;
+    return (int)(b < 1 ? 1 : b);
+}
+
+template <typename T>
+int launch_peer_update_rows(const PeerExchange& px, int64_t d, int k, const SolveArgs& a, T* colsum_part, int* flags,
+                            double* sums, unsigned* counter, int blocks, cudaStream_t st)
+{
+#define RRI_PEER(KM)                                                                                                  \
+    do {                                                                                                              \
+        const size_t smem = sizeof(T) * ((size_t)KM * KM + 2 * (size_t)TPR_ROWS * (KM + 1));                          \
+        auto kern = peer_update_rows_kernel<T, KM>;                                                                   \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        kern<<<blocks, TPR_ROWS, smem, st>>>(px, d, k, (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub,          \
+                                            colsum_part, flags, sums, counter);                                       \
+        return 1;                                                                                                     \
+    } while (0)
+    if (k <= 16) RRI_PEER(16);
+    if (k <= 32) RRI_PEER(32);
+    if (k <= 64) RRI_PEER(64);
+    if constexpr (sizeof(T) == 4) { if (k <= 128) RRI_PEER(128); }
+#undef RRI_PEER
+    return 0;                                          // rank too wide for the thread-per-row kernel: not fused
 }
 
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
                         const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft,
-                        T* colsum_part, int* flags, int blocks, cudaStream_t st)
+                        T* colsum_part, int* flags, int blocks, const ColsumOut& co, cudaStream_t st)
 {
     // thread-per-row variants while the row fits in registers / the tiles in shared memory
     // (fp32: k <= 128, fp64: k <= 64); wider ranks use the warp-per-row kernel
-#define RRI_TPR(KM) launch_update_rows_tpr<T, KM>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st)
+#define RRI_TPR(KM) launch_update_rows_tpr<T, KM>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, co, st)
     if (k <= 16) { RRI_TPR(16); return; }
     if (k <= 32) { RRI_TPR(32); return; }
     if (k <= 64) { RRI_TPR(64); return; }
     if (k <= 128 && sizeof(T) == 4) { RRI_TPR(128); return; }
 #undef RRI_TPR
     const int kl = (k + 31) / 32;
-    if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
-    else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
-    else if (kl <= 4) launch_update_rows_kl<T, 4>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
-    else launch_update_rows_kl<T, 8>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, st);
+    if (kl <= 1) launch_update_rows_kl<T, 1>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, co, st);
+    else if (kl <= 2) launch_update_rows_kl<T, 2>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, co, st);
+    else if (kl <= 4) launch_update_rows_kl<T, 4>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, co, st);
+    else launch_update_rows_kl<T, 8>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, co, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -633,7 +913,9 @@ void launch_transpose(const T* A, int64_t rows, int64_t cols, int64_t lda, T* B,
                                          int, cudaStream_t);                                              \
     template void launch_update_rows<T>(T*, int64_t, int, const T*, int, int64_t, const T* const*,        \
                                         const T*, const SolveArgs&, T*, int64_t, T*, int*, int,            \
-                                        cudaStream_t);                                                     \
+                                        const ColsumOut&, cudaStream_t);                                   \
+    template int launch_peer_update_rows<T>(const PeerExchange&, int64_t, int, const SolveArgs&, T*, int*,  \
+                                            double*, unsigned*, int, cudaStream_t);                        \
     template void launch_sum_sources<T>(const T* const*, int, int64_t, T*, cudaStream_t);                  \
     template void launch_gram<T>(const T*, int64_t, int, T*, int, T*, cudaStream_t);                      \
     template void launch_reduce_parts<T>(const T*, int, int64_t, int64_t, T*, cudaStream_t);              \

@@ -71,12 +71,39 @@ void launch_simt_gemm_nt(const T* A, int64_t lda, const T* B, int64_t ldb, T* Cp
 // C = sum of `parts` slices of Cpart.  Writes F in place, optionally Ft[k,m] = F', and per-block
 // column sums colsum_part[blocks][k].   (nmf.py:420-447 / :462-469 applied with the other factor frozen)
 int update_rows_blocks(int64_t m, int sm_count);
-// srcs (optional, device array of `parts` pointers): slice p is srcs[p] instead of Cpart + p*part_stride
-// (the peer-memory all-reduce of the multi-GPU T half-step reads every rank's partial in place).
+// Where the last block of an update kernel leaves the column sums: sums[off + t] (and the zero-topic flag bit
+// `zero_flag`, 0 = none); counter = device word that is zero between launches.  sums == nullptr: per-block partials only.
+struct ColsumOut {
+    double* sums;
+    int off, zero_flag;
+    unsigned* counter;
+};
+// srcs (optional, device array of `parts` pointers): slice p is srcs[p] instead of Cpart + p*part_stride.
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,
                         const T* const* srcs, const T* S, const SolveArgs& a, T* Ft, int64_t ldft,
-                        T* colsum_part, int* flags, int blocks, cudaStream_t st);
+                        T* colsum_part, int* flags, int blocks, const ColsumOut& co, cudaStream_t st);
+
+// Multi-GPU T half-step fused with its exchange over NVLink peer memory (hals_kernels.cu: peer_update_rows_kernel).
+// Pointers of rank r's exchange buffer as mapped in THIS process; flag arrays hold one 128-byte slot per rank.
+struct PeerExchange {
+    int world, rank;
+    unsigned epoch;
+    int64_t row_lo, row_hi;        // rows of T' (columns of T) this rank updates
+    int64_t ldtk;                  // row stride of the T replica [k, ldtk]
+    const void* part[16];          // this epoch's partial statistic of every rank: [d*k | k*k]
+    void* Tt[16];                  // every rank's replica of T' [d, k]
+    void* Tk[16];                  // every rank's replica of T  [k, ldtk]
+    void* tsum[16];                // every rank's table [world][k] of slice column sums
+    unsigned* flag1[16];           // every rank's "partials published" flags  [world x 32 words]
+    unsigned* flag2[16];           // every rank's "slice stored" flags         [world x 32 words]
+    int* err;
+};
+int peer_update_blocks(int64_t rows, int sm_count);
+// returns 1 (launched) or 0 (rank too wide for the fused kernel)
+template <typename T>
+int launch_peer_update_rows(const PeerExchange& px, int64_t d, int k, const SolveArgs& a, T* colsum_part, int* flags,
+                            double* sums, unsigned* counter, int blocks, cudaStream_t st);
 
 // out[c] = sum_p srcs[p][c] for c < len (fixed order) -- Gram partials of all ranks read through peer memory
 template <typename T>

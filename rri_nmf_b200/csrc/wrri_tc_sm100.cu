@@ -21,6 +21,7 @@
 
 #include "devmem.h"
 #include "kernels.h"
+#include "tc_sm100.cuh"
 #include "wrri_tc_sm100.h"
 
 namespace rri {
@@ -42,6 +43,7 @@ struct TcParams {
     const float* X; int64_t ldx;
     const void* M; int64_t ldm;
     const float* Wp; const float* Tp;      // padded operand copies [n,KP], [d,KP]
+    const float* Tt;                       // T[t, :] of the caller's factor (contiguous row), TMA variant
     int64_t n, d;
     int KP, t;
     int tiles_r, tiles_c;                  // number of 128-row / 128-column tiles
@@ -51,79 +53,8 @@ struct TcParams {
     int xm_stages;                         // TMA ring depth of the X / mask tiles (TMA variant)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) __trap();       // a protocol bug must not hang the GPU
-    }
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, void* dst, uint64_t* bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)      // K-major, SWIZZLE_128B (see gemm_tf32_sm100.cu)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
-{
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
+using namespace tc;
+
 __device__ __forceinline__ void epi_barrier()     // named barrier 1: the 8 epilogue warps only
 {
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
@@ -220,7 +151,7 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             }
             mbar_wait(fixed_full, 0);
             // D[128 rows of X, 64 columns of X] = W tile (A, M = 128) x T' tile (B, N = 64), TF32 in, FP32 out
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t idesc = make_idesc_tf32(TM, TN);
             for (int n = 0; n < ntiles; ++n) {
                 const int s = n % S, a = n & 1;
                 mbar_wait(&var_full[s], (n / S) & 1);
@@ -387,19 +318,44 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
 
 // ------------------------------------------------------------------------------------------------
-// TMA-staged variant (default): X and the mask are streamed by a dedicated producer thread into a ring of
-// shared-memory stages (cp.async.bulk.tensor, zero-filled tails), several tiles ahead of the epilogue, so no
-// warp ever waits on a dependent global load: warp 0 = operand TMA + MMA issue, warp 1 = X/mask producer,
-// warps 2-9 = epilogue.  One CTA per SM (the ring wants the shared memory).
+// TMA-staged variant (default).  Warp 0 = operand TMA + MMA issue, warp 1 = producer that streams the X tile and the
+// mask tile through a ring of shared-memory stages several tiles ahead, warps 2-17 = epilogue.  One CTA per SM.
+//
+// Epilogue without block barriers: epilogue warp (q, g) owns rows [32q, 32q+32) x columns [16g, 16g+16) of every
+// 128 x 64 tile.  It reads exactly that block of the product straight from TMEM into registers (one tcgen05.ld,
+// lane = row), the same elements of X from the stage -- written by TMA as two 32-column boxes with the 128-byte
+// swizzle, so that a row-per-lane 16-byte read is bank-conflict free -- and of the mask, keeps its partial sums in
+// registers across ALL tiles of the CTA, and hands the TMEM buffer and the stage back with one mbarrier arrival per
+// warp.  Warps drift across the two accumulator buffers and the ring stages instead of marching in lockstep; the
+// cross-warp reduction happens once per CTA.  (The previous version staged the product through shared memory between
+// two 512-thread barriers per tile: ~3400 cycles per tile where the HBM rate needs ~1750.)
 // ------------------------------------------------------------------------------------------------
 constexpr int EPI_WARPS_TMA = 16;                    // 4 warps per TMEM lane quarter (16 columns each)
 constexpr int THREADS_TMA = 32 * (2 + EPI_WARPS_TMA);
-constexpr int ROWS_TMA = TM / (2 * EPI_WARPS_TMA);  // row steps per thread in the element-wise pass
-constexpr int X_TILE_BYTES = TM * TN * 4;            // 32 KB
+constexpr int X_BOX_BYTES = TM * 32 * 4;             // one 32-column swizzled box of the X tile: 16 KB
+constexpr int X_TILE_BYTES = 2 * X_BOX_BYTES;        // 32 KB
 
 __device__ __forceinline__ void epi_barrier_tma()
 {
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS_TMA * 32) : "memory");
+}
+
+// 16 consecutive fp32 of row `row` starting at tile column c0 (multiple of 16) from a tile stored as two
+// [128 rows x 128 bytes] boxes with the 128-byte swizzle (16-byte chunk index XOR (row & 7))
+__device__ __forceinline__ void lds_row16_swz(const uint8_t* tile, int row, int c0, float v[16])
+{
+    const uint8_t* base = tile + (c0 >> 5) * X_BOX_BYTES + row * 128;
+    const int ch0 = (c0 & 31) >> 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(base + (((ch0 + j) ^ (row & 7)) << 4));
+        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+    }
+}
+// byte b (0..255) as a float without the conversion pipe: 0x4B000000 | b is 8388608 + b
+__device__ __forceinline__ float byte_to_float(uint32_t w, int i)
+{
+    return __uint_as_float(0x4B000000u | ((w >> (8 * i)) & 0xffu)) - 8388608.0f;
 }
 
 template <int MODE, int MK>
@@ -409,8 +365,8 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int M_TILE_BYTES = MK == MK_U8 ? TM * TN : TM * TN * 4;
-    constexpr int XM_STAGE = X_TILE_BYTES + M_TILE_BYTES;
+    constexpr int M_TILE_BYTES = MK == MK_U8 ? TM * TN : X_TILE_BYTES;
+    constexpr int XM_STAGE = X_TILE_BYTES + M_TILE_BYTES;            // 40 KB / 64 KB: a multiple of 1024
     const int nchunk = p.KP / BK;
     const int w_bytes = nchunk * W_CHUNK_BYTES, t_bytes = nchunk * T_CHUNK_BYTES;
     const int fixed_bytes = MODE == 0 ? t_bytes : w_bytes;
@@ -420,8 +376,7 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     uint8_t* sm_fixed = smem;
     uint8_t* sm_var = smem + fixed_bytes;
     uint8_t* sm_xm = sm_var + (size_t)p.stages * var_bytes;                       // [xm_stages][X tile | mask tile]
-    float* Ds = reinterpret_cast<float*>(sm_xm + (size_t)p.xm_stages * XM_STAGE);     // [TM][DS_LD]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Ds + TM * DS_LD);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm_xm + (size_t)p.xm_stages * XM_STAGE);
     uint64_t* fixed_full = bars;            // 1
     uint64_t* var_full = bars + 1;          // [2]
     uint64_t* var_free = bars + 3;          // [2]
@@ -445,9 +400,12 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 
     if (threadIdx.x == 0) {
         mbar_init(fixed_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&var_full[s], 1); mbar_init(&var_free[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 4); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&xm_full[s], 1); mbar_init(&xm_free[s], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&var_full[s], 1); mbar_init(&var_free[s], 1);
+            mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], EPI_WARPS_TMA);
+        }
+        for (int s = 0; s < 4; ++s) { mbar_init(&xm_full[s], 1); mbar_init(&xm_free[s], EPI_WARPS_TMA); }
+        fence_barrier_init();
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
@@ -472,7 +430,7 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                     tma_load_2d(tm_var, sm_var + (size_t)s0 * var_bytes + c * var_chunk, &var_full[s0], c * BK, (vb + s0) * var_rows);
             }
             mbar_wait(fixed_full, 0);
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            const uint32_t idesc = make_idesc_tf32(TM, TN);
             for (int n = 0; n < ntiles; ++n) {
                 const int s = n % S, a = n & 1;
                 mbar_wait(&var_full[s], (n / S) & 1);
@@ -505,137 +463,145 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             for (int n = 0; n < ntiles; ++n) {
                 const int s = n % NS;
                 const int rt = MODE == 0 ? (vb + n) : fixed_tile, ctile = MODE == 0 ? fixed_tile : (vb + n);
-                mbar_wait(&xm_free[s], ((n / NS) & 1) ^ 1);            // the epilogue has released this stage
+                mbar_wait(&xm_free[s], ((n / NS) & 1) ^ 1);            // every epilogue warp has released this stage
                 mbar_expect_tx(&xm_full[s], (uint32_t)XM_STAGE);
                 uint8_t* dst = sm_xm + (size_t)s * XM_STAGE;
                 tma_load_2d(&tmX, dst, &xm_full[s], ctile * TN, rt * TM);
-                tma_load_2d(&tmM, dst + X_TILE_BYTES, &xm_full[s], ctile * TN, rt * TM);
+                tma_load_2d(&tmX, dst + X_BOX_BYTES, &xm_full[s], ctile * TN + 32, rt * TM);
+                if (MK == MK_U8) {
+                    tma_load_2d(&tmM, dst + X_TILE_BYTES, &xm_full[s], ctile * TN, rt * TM);
+                } else {
+                    tma_load_2d(&tmM, dst + X_TILE_BYTES, &xm_full[s], ctile * TN, rt * TM);
+                    tma_load_2d(&tmM, dst + X_TILE_BYTES + X_BOX_BYTES, &xm_full[s], ctile * TN + 32, rt * TM);
+                }
             }
         }
     } else {
         // ======================================= epilogue ========================================
         const int ew = warp - 2;                 // 0..15
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
-        constexpr int R = ROWS_TMA;
-        constexpr int RSTEP = 2 * EPI_WARPS_TMA;     // rows covered by all warps in one step
-        const int cl = 4 * (lane & 15);
-        const int rsub = 2 * ew + (lane >> 4);
-        float nacc[MODE == 0 ? 4 : R], dacc[MODE == 0 ? 4 : R];
-#pragma unroll
-        for (int i = 0; i < (MODE == 0 ? 4 : R); ++i) { nacc[i] = 0.f; dacc[i] = 0.f; }
+        const int cgp = ew >> 2;                 // column group: tile columns [16*cgp, 16*cgp + 16)
+        const int row = q * 32 + lane;           // row of the tile this thread owns
+        const int c0 = 16 * cgp;
         const int NS = p.xm_stages;
+        const float* Trow = p.Tt;                // T[t, :] (contiguous), W[:, t] = Wp[:, t] (stride KP)
 
-        // row t of T' and column t of W for this thread's columns / rows of a tile: the only global loads left in
-        // the epilogue (L2-resident factors).  They are requested one tile ahead so their latency never shows.
-        auto load_factors = [&](int n, float tt_out[4], float wts_out[R]) {
-            const int rt = MODE == 0 ? (vb + n) : fixed_tile, ctile = MODE == 0 ? fixed_tile : (vb + n);
-            const int64_t i0 = (int64_t)rt * TM, gc = (int64_t)ctile * TN + cl;
-            const bool ok = n < ntiles;
+        // MODE 0: per-column accumulators (this thread's row only) kept over all row tiles; MODE 1: one per row
+        float nacc[MODE == 0 ? 16 : 1], dacc[MODE == 0 ? 16 : 1];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) tt_out[v] = (ok && gc < p.d) ? __ldg(p.Tp + (gc + v) * p.KP + p.t) : 0.f;
+        for (int i = 0; i < (MODE == 0 ? 16 : 1); ++i) { nacc[i] = 0.f; dacc[i] = 0.f; }
+
+        // factor entries of topic t for this thread's columns / row.  The fixed side is loaded once; the side that
+        // changes with the tile is requested one tile ahead.
+        float tt[16];
+        float wt = 0.f;
+        auto load_tt = [&](int ctile, float out[16]) {
+            const int64_t gc = (int64_t)ctile * TN + c0;
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                const int64_t gi = i0 + rsub + RSTEP * rr;
-                wts_out[rr] = (ok && gi < p.n) ? __ldg(p.Wp + gi * p.KP + p.t) : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gc + 4 * j < p.d) v = __ldg(reinterpret_cast<const float4*>(Trow + gc) + j);     // d % 4 == 0
+                out[4 * j] = v.x; out[4 * j + 1] = v.y; out[4 * j + 2] = v.z; out[4 * j + 3] = v.w;
             }
         };
-        float tt[4], wts[R];
-        load_factors(0, tt, wts);
+        auto load_wt = [&](int rt) -> float {
+            const int64_t gi = (int64_t)rt * TM + row;
+            return gi < p.n ? __ldg(p.Wp + gi * p.KP + p.t) : 0.f;
+        };
+        float ttn[MODE == 1 ? 16 : 1];
+        float wtn = 0.f;
+        if (MODE == 0) { load_tt(fixed_tile, tt); wt = ntiles > 0 ? load_wt(vb) : 0.f; }
+        else { wt = load_wt(fixed_tile); if (ntiles > 0) load_tt(vb, tt); }
 
         for (int n = 0; n < ntiles; ++n) {
             const int a = n & 1, s = n % NS;
-            float ttn[4], wtsn[R];
-            load_factors(n + 1, ttn, wtsn);
+            if (n + 1 < ntiles) {
+                if (MODE == 0) wtn = load_wt(vb + n + 1);
+                else load_tt(vb + n + 1, ttn);
+            }
+            // ---- this warp's 32 x 16 block of the product: TMEM -> registers
             mbar_wait(&acc_full[a], (n >> 1) & 1);
             tc_fence_after();
-            {   // TMEM -> shared: the four warps of a lane quarter take 16 columns each
-                const int col = (ew >> 2) * 16;
-                const int row = q * 32 + lane;
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + col), v);
-                float4* o = reinterpret_cast<float4*>(Ds + row * DS_LD + col);
-                o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                o[1] = make_float4(v[4], v[5], v[6], v[7]);
-                o[2] = make_float4(v[8], v[9], v[10], v[11]);
-                o[3] = make_float4(v[12], v[13], v[14], v[15]);
+            uint32_t dr[16];
+            tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), dr);
+            // ---- the same block of X and of the mask from the stage
+            mbar_wait(&xm_full[s], (n / NS) & 1);
+            const uint8_t* stage = sm_xm + (size_t)s * XM_STAGE;
+            float x[16], m[16];
+            lds_row16_swz(stage, row, c0, x);
+            if (MK == MK_U8) {
+                const uint4 mw = *reinterpret_cast<const uint4*>(stage + X_TILE_BYTES + row * TN + c0);
+                const uint32_t w4[4] = {mw.x, mw.y, mw.z, mw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) m[4 * j + v] = byte_to_float(w4[j], v);
+            } else {
+                lds_row16_swz(stage + X_TILE_BYTES, row, c0, m);
             }
-            mbar_wait(&xm_full[s], (n / NS) & 1);                     // this tile's X and mask have landed
+            tmem_ld_wait();
             tc_fence_before();
-            epi_barrier_tma();                                        // product tile staged; TMEM reads done
-            if (lane == 0 && ew < 4) mbar_arrive(&acc_free[a]);
-
-            const float* Xs = reinterpret_cast<const float*>(sm_xm + (size_t)s * XM_STAGE);
-            const uint8_t* Ms = sm_xm + (size_t)s * XM_STAGE + X_TILE_BYTES;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[a]);                 // the accumulator block is in registers
+            // ---- element-wise statistics: M o (X - W_{t->0} T) with topic t added back in fp32
+            const float ww = wt * wt;
+            float nrow = 0.f, drow = 0.f;
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                const int r = rsub + RSTEP * rr;
-                float m[4];
-                bool any;
-                if (MK == MK_U8) {
-                    const uint32_t w = *reinterpret_cast<const uint32_t*>(Ms + r * TN + cl);
-                    any = w != 0u;
-                    m[0] = (float)(w & 0xffu); m[1] = (float)((w >> 8) & 0xffu); m[2] = (float)((w >> 16) & 0xffu); m[3] = (float)(w >> 24);
+            for (int c = 0; c < 16; ++c) {
+                const float res = m[c] * (x[c] - __uint_as_float(dr[c]) + wt * tt[c]);
+                if (MODE == 0) {
+                    nacc[c] = fmaf(wt, res, nacc[c]);
+                    dacc[c] = fmaf(ww, m[c], dacc[c]);
                 } else {
-                    const float4 mv = *reinterpret_cast<const float4*>(Ms + (size_t)(r * TN + cl) * 4);
-                    m[0] = mv.x; m[1] = mv.y; m[2] = mv.z; m[3] = mv.w;
-                    any = (mv.x != 0.f) | (mv.y != 0.f) | (mv.z != 0.f) | (mv.w != 0.f);
-                }
-                if (any) {
-                    const float4 xv = *reinterpret_cast<const float4*>(Xs + r * TN + cl);
-                    const float4 dv = *reinterpret_cast<const float4*>(Ds + r * DS_LD + cl);
-                    const float wt = wts[rr];
-                    const float x[4] = {xv.x, xv.y, xv.z, xv.w};
-                    const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const float res = m[v] * (x[v] - dd[v] + wt * tt[v]);          // M o (X - W_{t->0} T)
-                        if (MODE == 0) {
-                            nacc[v] = fmaf(wt, res, nacc[v]);
-                            dacc[v] = fmaf(wt * wt, m[v], dacc[v]);
-                        } else {
-                            nacc[rr] = fmaf(res, tt[v], nacc[rr]);
-                            dacc[rr] = fmaf(m[v] * tt[v], tt[v], dacc[rr]);
-                        }
-                    }
+                    nrow = fmaf(res, tt[c], nrow);
+                    drow = fmaf(m[c] * tt[c], tt[c], drow);
                 }
             }
-            epi_barrier_tma();                                        // Ds and this X/mask stage are free again
-            if (ew == 0 && lane == 0) mbar_arrive(&xm_free[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&xm_free[s]);                  // every lane has consumed its X / mask values
+            if (MODE == 1) { nacc[0] += nrow; dacc[0] += drow; }
+            if (MODE == 0) wt = wtn;
+            else {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) tt[v] = ttn[v];
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) wts[rr] = wtsn[rr];
+                for (int c = 0; c < 16; ++c) tt[c] = ttn[c];
+            }
         }
 
+        // ---- once per CTA: cross-warp reduction through the (now idle) stage buffers, fixed order
+        epi_barrier_tma();
+        float* red = reinterpret_cast<float*>(sm_xm);
+        const int et = threadIdx.x - 64;                              // 0..511
         if (MODE == 0) {
-            float* red = Ds;                                          // [2*EPI_WARPS_TMA][2][TN]
-            const int slot = 2 * ew + (lane >> 4);
+            // red[which][col 0..63][row 0..127]: column sums over the 128 rows of the tile position
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                red[(slot * 2 + 0) * TN + cl + v] = nacc[v];
-                red[(slot * 2 + 1) * TN + cl + v] = dacc[v];
+            for (int c = 0; c < 16; ++c) {
+                red[(0 * TN + c0 + c) * TM + row] = nacc[c];
+                red[(1 * TN + c0 + c) * TM + row] = dacc[c];
             }
             epi_barrier_tma();
-            const int e = threadIdx.x - 64;                           // 0..511
-            if (e < 2 * TN) {
-                const int which = e / TN, cc = e % TN;
-                float sacc = 0.f;
-#pragma unroll
-                for (int w = 0; w < 2 * EPI_WARPS_TMA; ++w) sacc += red[(w * 2 + which) * TN + cc];
+            // 512 threads, 128 outputs: 4 threads per output add 32 rows each, then a 4-lane shuffle tree
+            const int o = et >> 2, part = et & 3;
+            float sacc = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) sacc += red[o * TM + part * 32 + ((r + 8 * part) & 31)];
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+            sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            if (part == 0) {
+                const int which = o / TN, cc = o % TN;
                 const int64_t gcol = (int64_t)fixed_tile * TN + cc;
                 if (gcol < p.d) (which ? p.denom_part : p.numer_part)[(int64_t)blockIdx.y * p.d + gcol] = sacc;
             }
         } else {
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                float a = nacc[rr], b = dacc[rr];
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-                const int64_t gi = (int64_t)fixed_tile * TM + rsub + RSTEP * rr;
-                if ((lane & 15) == 0 && gi < p.n) {
-                    p.numer_part[(int64_t)blockIdx.y * p.n + gi] = a;
-                    p.denom_part[(int64_t)blockIdx.y * p.n + gi] = b;
-                }
+            // red[which][column group][row]
+            red[(0 * 4 + cgp) * TM + row] = nacc[0];
+            red[(1 * 4 + cgp) * TM + row] = dacc[0];
+            epi_barrier_tma();
+            if (et < 2 * TM) {
+                const int which = et / TM, r = et % TM;
+                const float sacc = (red[(which * 4 + 0) * TM + r] + red[(which * 4 + 1) * TM + r]) +
+                                   (red[(which * 4 + 2) * TM + r] + red[(which * 4 + 3) * TM + r]);
+                const int64_t gi = (int64_t)fixed_tile * TM + r;
+                if (gi < p.n) (which ? p.denom_part : p.numer_part)[(int64_t)blockIdx.y * p.n + gi] = sacc;
             }
         }
     }
@@ -771,31 +737,37 @@ static bool tma_prepare(WrriTc* g, const float* X, int64_t ldx, const void* M, i
     g->mapX = X; g->mapM = M; g->map_ldx = ldx; g->map_ldm = ldm; g->map_mk = mk; g->tma_ok = false;
     const size_t mes = mk == MK_U8 ? 1 : 4;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (ldx * 4) % 16 || (reinterpret_cast<uintptr_t>(M) & 15) || (ldm * mes) % 16) return false;
-    auto enc = [&](CUtensorMap* tm, const void* base, CUtensorMapDataType dt, size_t es, int64_t ld) -> bool {
+    // fp32 tiles are fetched as 32-column boxes with the 128-byte swizzle (conflict-free row-per-lane reads in the
+    // epilogue); the byte mask as one unswizzled 64-column box
+    auto enc = [&](CUtensorMap* tm, const void* base, CUtensorMapDataType dt, size_t es, int64_t ld, int box_cols,
+                   CUtensorMapSwizzle sw) -> bool {
         cuuint64_t gdim[2] = {(cuuint64_t)g->d, (cuuint64_t)g->n};
         cuuint64_t gstr[1] = {(cuuint64_t)ld * es};
-        cuuint32_t box[2] = {(cuuint32_t)TN, (cuuint32_t)TM};
+        cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)TM};
         cuuint32_t estr[2] = {1, 1};
-        return g->encode(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        return g->encode(tm, dt, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
-    if (!enc(&g->tmX, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ldx)) return false;
-    if (!enc(&g->tmM, M, mk == MK_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, mes, ldm)) return false;
-    // shared-memory plan per mode: operands + product tile + as many X/mask stages as fit (at least 2)
+    if (!enc(&g->tmX, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ldx, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+    if (mk == MK_U8) {
+        if (!enc(&g->tmM, M, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ldm, TN, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+    } else {
+        if (!enc(&g->tmM, M, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ldm, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
+    }
+    // shared-memory plan per mode: operands + as many X/mask stages as fit (at least 2) + barriers
     const int w_bytes = (g->KP / BK) * W_CHUNK_BYTES, t_bytes = (g->KP / BK) * T_CHUNK_BYTES;
-    const size_t ds = sizeof(float) * TM * DS_LD + 512 + 1024;
-    const size_t xm = (size_t)X_TILE_BYTES + (mk == MK_U8 ? (size_t)TM * TN : (size_t)TM * TN * 4);
+    const size_t extra = 1024 /* barriers */ + 1024 /* alignment slack */;
+    const size_t xm = (size_t)X_TILE_BYTES + (mk == MK_U8 ? (size_t)TM * TN : (size_t)X_TILE_BYTES);
     for (int mode = 0; mode < 2; ++mode) {
         const size_t fixed = mode == 0 ? t_bytes : w_bytes, var = mode == 0 ? w_bytes : t_bytes;
         // two operand stages first (with one, every tile waits a full L2 round trip for its W / T' tile after the
-        // previous MMA retires: measured 1.75 us per tile), then as many X/mask stages as still fit (>= 2)
+        // previous MMA retires), then as many X/mask stages as still fit (>= 2; the end-of-CTA reduction needs 64 KB)
         const size_t room = (size_t)227 * 1024;
         int S = 0, ns = 0;
         static const char* force_s = getenv("RRI_WRRI_OPERAND_STAGES");
         for (int s_try = 2; s_try >= 1; --s_try) {
             if (force_s && atoi(force_s) != s_try) continue;
-            const size_t base = fixed + (size_t)s_try * var + ds;
+            const size_t base = fixed + (size_t)s_try * var + extra;
             if (base >= room) continue;
             int n_try = (int)((room - base) / xm);
             if (n_try > 4) n_try = 4;
@@ -804,25 +776,27 @@ static bool tma_prepare(WrriTc* g, const float* X, int64_t ldx, const void* M, i
         if (S < 1 || ns < 2) { g->tma_xm[mode][mk] = 0; continue; }
         g->tma_stages[mode][mk] = S;
         g->tma_xm[mode][mk] = ns;
-        g->tma_smem[mode][mk] = fixed + (size_t)S * var + ds + (size_t)ns * xm;
+        g->tma_smem[mode][mk] = fixed + (size_t)S * var + extra + (size_t)ns * xm;
     }
     g->tma_ok = true;
     return true;
 }
 
 template <int MODE>
-static int launch_mode(WrriTc* g, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm, int t, float* numer_part,
-                       float* denom_part, int groups, cudaStream_t st, std::string& err)
+static int launch_mode(WrriTc* g, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm, int t, const float* Trow,
+                       float* numer_part, float* denom_part, int groups, cudaStream_t st, std::string& err)
 {
     TcParams p;
     p.X = X; p.ldx = ldx; p.M = M; p.ldm = ldm; p.Wp = g->Wp; p.Tp = g->Tp; p.n = g->n; p.d = g->d; p.KP = g->KP; p.t = t;
+    p.Tt = Trow;
     p.tiles_r = (int)((g->n + TM - 1) / TM); p.tiles_c = (int)((g->d + TN - 1) / TN);
     p.groups = groups; p.numer_part = numer_part; p.denom_part = denom_part; p.stages = g->stages[MODE]; p.xm_stages = 0;
     dim3 grid(MODE == 0 ? p.tiles_c : p.tiles_r, groups);
     if (mk != MK_U8 && mk != MK_REAL) { err = "the tensor-core WRRI path needs a mask"; return -1; }
     if (ldm % 4 != 0) { err = "mask rows need a stride that is a multiple of 4 elements"; return -1; }
     static const bool no_tma = getenv("RRI_WRRI_NO_TMA") != nullptr;
-    if (!no_tma && tma_prepare(g, X, ldx, M, mk, ldm) && g->tma_xm[MODE][mk] >= 2) {
+    if (!no_tma && Trow && (reinterpret_cast<uintptr_t>(Trow) & 15) == 0 && tma_prepare(g, X, ldx, M, mk, ldm) &&
+        g->tma_xm[MODE][mk] >= 2) {
         p.stages = g->tma_stages[MODE][mk];
         p.xm_stages = g->tma_xm[MODE][mk];
         const size_t smem = g->tma_smem[MODE][mk];
@@ -850,11 +824,11 @@ static int launch_mode(WrriTc* g, const float* X, int64_t ldx, const void* M, in
 }
 
 int wrri_tc_stats(WrriTc* g, int mode, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm, int t,
-                  float* numer_part, float* denom_part, int groups, cudaStream_t st, std::string& err)
+                  const float* Trow, float* numer_part, float* denom_part, int groups, cudaStream_t st, std::string& err)
 {
     if ((reinterpret_cast<uintptr_t>(X) & 15) != 0 || ldx % 4 != 0) { err = "X rows must be 16-byte aligned"; return -1; }
-    return mode == 0 ? launch_mode<0>(g, X, ldx, M, mk, ldm, t, numer_part, denom_part, groups, st, err)
-                     : launch_mode<1>(g, X, ldx, M, mk, ldm, t, numer_part, denom_part, groups, st, err);
+    return mode == 0 ? launch_mode<0>(g, X, ldx, M, mk, ldm, t, Trow, numer_part, denom_part, groups, st, err)
+                     : launch_mode<1>(g, X, ldx, M, mk, ldm, t, Trow, numer_part, denom_part, groups, st, err);
 }
 
 }  // namespace rri

@@ -15,6 +15,7 @@ int wrri_tc_groups(WrriTc* g, int mode);           // partial slices written by 
 void wrri_tc_load_factors(WrriTc* g, const float* W, const float* T, cudaStream_t st);
 // mode 0: numer_part/denom_part[groups][d] (nmf.py:700-701); mode 1: [groups][n] (nmf.py:745-746).
 // returns the number of kernels launched or -1
+// Trow = row t of the caller's T (k x d, contiguous row of d floats).
 int wrri_tc_stats(WrriTc* g, int mode, const float* X, int64_t ldx, const void* M, int mk, int64_t ldm, int t,
-                  float* numer_part, float* denom_part, int groups, cudaStream_t st, std::string& err);
+                  const float* Trow, float* numer_part, float* denom_part, int groups, cudaStream_t st, std::string& err);
 }  // namespace rri

@@ -296,10 +296,11 @@ class RRIEngine(object):
 
     def profile_kernel(self, which, W, T, iters=5):
         """average launch duration (ms) of the dominant streaming kernel, timed with CUDA events on the
-        launching stream: which in {'rri_pass', 'gemm_w', 'gemm_t'}"""
+        launching stream: which in {'rri_pass', 'gemm_w', 'gemm_t'}; 't_half' / 'w_half' time a whole
+        block-order half-step (they advance W, T and are collective on row shards)"""
         self._check_factors(W, T)
         ms = C.c_float(0)
-        idx = {'rri_pass': 0, 'gemm_w': 1, 'gemm_t': 2}[which]
+        idx = {'rri_pass': 0, 'gemm_w': 1, 'gemm_t': 2, 't_half': 3, 'w_half': 4}[which]
         check(self.lib.rri_profile_kernel(self.h, idx, _ptr(W), _ptr(T), int(iters), C.byref(ms), self._stream()))
         return float(ms.value)
 
