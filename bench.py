@@ -361,6 +361,42 @@ def main_ours(args):
         except Exception as ex:
             roofline['half_steps_ms'] = {'error': repr(ex)[:200]}
 
+    objective_cost = None
+    if args.order == 'hals':
+        # an objective per sweep (compute_obj_each_iter=True): the explicit pass over X against the form that
+        # reuses the sweep's own contraction
+        try:
+            Wc, Tc = W.clone(), T.clone()
+
+            def timed(fn, reps):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a0.record()
+                for _ in range(reps):
+                    fn()
+                a1.record()
+                torch.cuda.synchronize()
+                return a0.elapsed_time(a1) / reps
+
+            def sweep_and_obj():
+                eng.sweeps(Wc, Tc, 1, params, want_flags=False)
+                return eng.objective(Wc, Tc, via_contraction=True, reuse_last_sweep=True)
+
+            sweep_and_obj()
+            t_both = timed(sweep_and_obj, 5)
+            t_sweep = timed(lambda: eng.sweeps(Wc, Tc, 1, params, want_flags=False), 5)
+            eng.sweeps(Wc, Tc, 1, params, want_flags=False)
+            o_fast = eng.objective(Wc, Tc, via_contraction=True, reuse_last_sweep=True)
+            o_exact = eng.objective(Wc, Tc)
+            t_exact = timed(lambda: eng.objective(Wc, Tc), 2)
+            objective_cost = {'ms_sweep': t_sweep, 'ms_sweep_plus_objective_via_contraction': t_both,
+                              'overhead_frac': t_both / t_sweep - 1.0, 'ms_explicit_objective_pass': t_exact,
+                              'objective_via_contraction': o_fast, 'objective_explicit': o_exact,
+                              'rel_diff': o_fast / o_exact - 1.0, 'world_local_terms_only': world > 1}
+            del Wc, Tc
+        except Exception as ex:
+            objective_cost = {'error': repr(ex)[:200]}
+
     # ---- e2e: the public call with HOST buffers, copies inside the timed region.  Two figures: pinned host arrays
     # (the headline e2e) and plain pageable NumPy arrays (what a drop-in user passes; nmf() stages them through
     # its own pinned chunk buffers)
@@ -457,7 +493,7 @@ def main_ours(args):
                        'final_rel_error': relerr,
                        'exchange': ('nvlink peer memory (fused into the T update)' if peer_x else 'nccl all-reduce') if world > 1 else 'none'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
-            'reference_order': rri_side,
+            'reference_order': rri_side, 'objective_per_sweep': objective_cost,
         }
         if cpu and rri_side and rri_side.get('value'):
             # same update order on both sides: the reference's interleaved sweep on the GPU over the CPU figure

@@ -45,8 +45,11 @@ typedef struct rri_params_s {
     double eps;            /* eps_div_by_zero = np.spacing(10), nmf.py:52, optimization.py:5 */
     int32_t fix_W, fix_T;  /* nmf.py:417, :460.  fix_T = W-only sweeps (transform()).  fix_W must be 0: the reference's
                               T-only sweep also rescales W (:450-452); the host shell drives it from rri_partials_T */
-    int32_t simplex_T;     /* project_T_each_iter with s = ub_t: optimization.py:58-59 + nmf.py:759-761 */
-    int32_t reserved;
+    int32_t simplex_T;     /* project_T_each_iter with s = ub_t: optimization.py:58-59 + nmf.py:759-761 (unmasked);
+                              optimization.py:85-87 (masked / observed entries: rescale the clipped solution to sum s) */
+    int32_t sp_refresh_every;  /* observed-entries handles, interleaved order: rebuild the residual copies from the factors
+                              every this many sweeps of one rri_sweeps call (0 / 1 = every sweep: N sweeps in one call
+                              == N calls of one sweep, bit for bit) */
 } rri_params_t;
 
 /* library / build information; never touches the GPU (safe on a CPU-only host) */
@@ -125,6 +128,17 @@ int rri_topic_sums(rri_handle_t h, double* sum_T_host, double* sum_W_host, void*
  * out_host[4] = sum T^2, out_host[5] = sum |T|.  The caller combines them with the regularisers
  * (and all-reduces entries 0-3 across shards). */
 int rri_objective(rri_handle_t h, const void* W_dev, const void* T_dev, double* out_host, void* stream);
+
+/* The same six numbers for UNMASKED dense data without a pass over X per call:
+ *     ||X - W T||^2 = ||X||^2 - 2 <X T', W> + <W'W, T T'>          (fp64 sums; ||X||^2 once per binding)
+ * where X T' is the contraction of the W half-step.  reuse_last_sweep != 0 states that W_dev / T_dev are exactly what
+ * the last rri_sweeps call on a block-order handle left, so that call's own contraction is reused (an objective per
+ * sweep then costs two k x k Gram products and one dot product over n*k, ~3 % of a config-3 sweep, instead of the
+ * reference's "2x penalty", nmf.py:143-146); otherwise one contraction pass is made.  The difference of large terms
+ * inherits the contraction's rounding: exact to ~1e-12 relative in fp64, ~1e-5 in IEEE fp32, and with TF32 operands
+ * the relative error of <X T', W> (~1e-6) is amplified by ||X||^2 / ||X - WT||^2. */
+int rri_objective_contraction(rri_handle_t h, const void* W_dev, const void* T_dev, int32_t reuse_last_sweep,
+                              double* out_host, void* stream);
 
 /* Test hook == the partial statistic of nmf.py:680-686 (unmasked) / :706-713 (masked) for the local
  * rows: out_wR_dev[d], out_nw_dev[1 (unmasked) | d (masked)], same dtype as X. */

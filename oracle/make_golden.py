@@ -76,6 +76,17 @@ def make_fix_W(ref):
     np.savez_compressed(os.path.join(OUT, 'fixW_f64.npz'), **d)
 
 
+def estimator_goldens(ref, Xr):
+    """The reference's recommender estimator on its own fixture (tests/test_nmf.py:81-88): NNDSVD init, 5 % validation
+    split, validation-RMSE early stop (it stops after 2 sweeps and reverts to the state after the first).  Depends on
+    sklearn's randomized_svd and train_test_split, like the replay scalars."""
+    n, d = Xr.shape
+    E = ref.sklearn_interface.NMF_RS_Estimator(n, d, 5, random_state=0, max_iter=20)
+    E = E.fit_from_Xtr(scipy.sparse.csr_matrix(Xr))
+    np.savez_compressed(os.path.join(OUT, 'rs_estimator_f64.npz'), W=E.W, T=E.T,
+                        obj_history=np.array(E.nmf_outputs['obj_history']), score=np.array([E.score(Xr)]))
+
+
 def main():
     ref = refshim.load()
     os.makedirs(OUT, exist_ok=True)
@@ -210,6 +221,7 @@ def main():
                         t_row_sum=1.0, project_W_each_iter=False, w_row_sum=None, **regs)
         rep[name] = np.array(r['obj_history'])
     np.savez_compressed(os.path.join(OUT, 'replay_scalars.npz'), **rep)
+    estimator_goldens(ref, Xr)
     print('golden written to', os.path.abspath(OUT))
     for f in sorted(os.listdir(OUT)):
         print('  %-32s %8d B' % (f, os.path.getsize(os.path.join(OUT, f))))

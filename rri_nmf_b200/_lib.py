@@ -20,7 +20,7 @@ class RriParams(C.Structure):
     """rri_params_t (include/rri_b200.h)"""
     _fields_ = [('reg_w_l1', C.c_double), ('reg_w_l2', C.c_double), ('reg_t_l1', C.c_double),
                 ('reg_t_l2', C.c_double), ('ub_w', C.c_double), ('ub_t', C.c_double), ('eps', C.c_double),
-                ('fix_W', C.c_int32), ('fix_T', C.c_int32), ('simplex_T', C.c_int32), ('reserved', C.c_int32)]
+                ('fix_W', C.c_int32), ('fix_T', C.c_int32), ('simplex_T', C.c_int32), ('sp_refresh_every', C.c_int32)]
 
 
 # every symbol include/rri_b200.h declares: name -> (restype, argtypes)
@@ -45,6 +45,7 @@ SYMBOLS = {
     'rri_topics': (C.c_int, [_vp, _vp, _vp, _i32, _i32, C.POINTER(RriParams), C.POINTER(_i32), _vp]),
     'rri_topic_sums': (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), _vp]),
     'rri_objective': (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_double), _vp]),
+    'rri_objective_contraction': (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(C.c_double), _vp]),
     'rri_partials_T': (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     'rri_project_rows_simplex': (C.c_int, [_vp, _vp, _i64, _i64, C.c_double, _vp]),
     'rri_cache_trim': (C.c_int, [_i32]),

@@ -179,6 +179,10 @@ struct rri_handle_s {
     int* flags = nullptr;      // device
     double *obj_part = nullptr, *obj_out = nullptr;
     int oblocks = 1;
+    // objective through the contraction: ||X||^2 is computed once per binding; c2_valid = Cpart still holds X T' of
+    // the current T (and Tt its transpose): true right after a block-order sweep
+    bool xsq_valid = false, c2_valid = false;
+    void* Gobj = nullptr;
 };
 
 static int ws_alloc(rri_handle_t h, void** p, size_t bytes)
@@ -448,8 +452,10 @@ static int bind_impl(rri_handle_t h, cudaStream_t st)
     const size_t es = sizeof(T);
     h->oblocks = obj_blocks(n, d, h->sm_count);
     if (!h->obj_part) {
-        if (ws_alloc(h, (void**)&h->obj_part, sizeof(double) * 2 * (size_t)(h->oblocks > 256 ? h->oblocks : 256))) return 1;
-        if (ws_alloc(h, (void**)&h->obj_out, sizeof(double) * 8)) return 1;
+        size_t op = 2 * (size_t)(h->oblocks > 256 ? h->oblocks : 256);
+        if (op < (size_t)8 * h->sm_count) op = (size_t)8 * h->sm_count;
+        if (ws_alloc(h, (void**)&h->obj_part, sizeof(double) * op)) return 1;
+        if (ws_alloc(h, (void**)&h->obj_out, sizeof(double) * 16)) return 1;
     }
     if (h->mk != MK_NONE) {
         if (!h->numer_part) {
@@ -560,6 +566,7 @@ extern "C" int rri_bind(rri_handle_t h, const void* X_dev, int64_t ldX, const vo
     h->M = mask_kind == RRI_MASK_NONE ? nullptr : mask_dev;
     h->mk = mask_kind; h->ldm = ldM;
     h->fixT_cached = false;
+    h->xsq_valid = false; h->c2_valid = false;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = h->dtype == RRI_F32 ? bind_impl<float>(h, st) : bind_impl<double>(h, st);
     if (rc) return rc;
@@ -1091,11 +1098,14 @@ static int sp_load_factors(rri_handle_t h, const T* W, const T* Tm, cudaStream_t
 }
 
 template <typename T>
-static int sp_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri_params_t* p, cudaStream_t st)
+static int sp_topic_range(rri_handle_t h, T* W, T* Tm, int t0, int t1, const rri_params_t* p, cudaStream_t st,
+                          SpState* carried = nullptr, bool restart = true)
 {
-    // reference order (nmf.py:415-476); both residual copies restart from the current factors
-    SpState S;
-    sp_refresh<T>(h, true, true, W, st);
+    // reference order (nmf.py:415-476).  restart: both residual copies are rebuilt from the current factors (always at
+    // the start of a call); otherwise they continue from the previous sweep with its pending rank-one record
+    SpState local;
+    SpState& S = carried ? *carried : local;
+    if (restart) { S = SpState(); sp_refresh<T>(h, true, true, W, st); }
     for (int t = t0; t < t1; ++t) {
         if (sp_T_step<T>(h, W, Tm, t, p, S, st)) return 1;
         if (sp_W_step<T>(h, W, Tm, t, p, S, st)) return 1;
@@ -1110,9 +1120,15 @@ static int sp_sweeps(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_params
 {
     const int k = h->k;
     if (sp_load_factors<T>(h, W, Tm, st)) return 1;
+    // residual restart period inside one call (rri_params_t.sp_refresh_every; 0 or 1 = every sweep, which makes
+    // N sweeps in one call == N calls of one sweep bit for bit).  The restart costs 17 % of a config-4 sweep; with a
+    // longer period the two residual copies are carried from sweep to sweep (interleaved order only: in block order
+    // each half updates one copy k times while the other stands still).
+    const int every = p->sp_refresh_every > 1 ? p->sp_refresh_every : 1;
+    SpState carried;
     for (int s = 0; s < n_sweeps; ++s) {
         if (!p->fix_T && h->order == RRI_ORDER_RRI) {
-            if (sp_topic_range<T>(h, W, Tm, 0, k, p, st)) return 1;
+            if (sp_topic_range<T>(h, W, Tm, 0, k, p, st, &carried, s % every == 0)) return 1;
             continue;
         }
         if (!p->fix_T) {                       // block order, T half: only the column copy is read
@@ -1184,6 +1200,7 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
         }
         if (px) CK(cudaMemcpy2DAsync(Tm, (size_t)d * sizeof(T), Tk, (size_t)ldtk * sizeof(T), (size_t)d * sizeof(T), (size_t)k,
                                      cudaMemcpyDeviceToDevice, st));
+        h->c2_valid = n_sweeps > 0;            // Cpart = X T' for the T just written, Tt = its transpose
         return hals_finish_sums(h, st);
     }
     if (rri_prologue<T>(h, W, 0, p, st)) return 1;
@@ -1210,6 +1227,7 @@ extern "C" int rri_sweeps(rri_handle_t h, void* W_dev, void* T_dev, int32_t n_sw
     CK(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemsetAsync(h->flags, 0, sizeof(int), st));
+    h->c2_valid = false;
     if (n_sweeps > 0) {
         int rc = h->dtype == RRI_F32 ? sweeps_impl<float>(h, (float*)W_dev, (float*)T_dev, n_sweeps, p, st)
                                      : sweeps_impl<double>(h, (double*)W_dev, (double*)T_dev, n_sweeps, p, st);
@@ -1302,6 +1320,62 @@ extern "C" int rri_objective(rri_handle_t h, const void* W_dev, const void* T_de
     cudaStream_t st = (cudaStream_t)stream;
     int rc = h->dtype == RRI_F32 ? objective_impl<float>(h, (const float*)W_dev, (const float*)T_dev, st)
                                  : objective_impl<double>(h, (const double*)W_dev, (const double*)T_dev, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_host, h->obj_out, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Objective through the contraction (unmasked dense data):  ||X - W T||^2 = ||X||^2 - 2 <X T', W> + <W'W, T T'>.
+// reuse != 0: the caller states that W and T are exactly what the last rri_sweeps call (block order) left, so the
+// contraction X T' of its last W half-step is still in the workspace; otherwise one contraction pass is made.
+template <typename T>
+static int objective_contraction_impl(rri_handle_t h, const T* W, const T* Tm, bool reuse, cudaStream_t st)
+{
+    const int64_t n = h->n, d = h->d;
+    const int k = h->k;
+    if (!h->Gobj && ws_alloc(h, &h->Gobj, sizeof(T) * 2 * (size_t)k * k)) return 1;
+    CK(cudaStreamSynchronize(0));
+    double* acc = h->obj_out + 8;                       // {||X||^2, <X T', W>}
+    if (!h->xsq_valid) {
+        launch_sumsq_rows<T>((const T*)h->X, n, d, h->ldx, h->obj_part, acc, h->sm_count, st);
+        h->xsq_valid = true;
+        h->launches += 2;
+    }
+    if (!(reuse && h->c2_valid)) {
+        launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
+        h->launches++;
+        if (contraction<T>(h, (const T*)h->X, h->ldx, Tm, d, (T*)h->Cpart, n, k, d, h->splits_w, st)) return 1;
+        h->c2_valid = false;                            // (the caller's T may change before the next call)
+    }
+    const int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_w;
+    launch_dot_parts<T>((const T*)h->Cpart, parts, n * k, W, n * k, h->obj_part, acc + 1, h->sm_count, st);
+    T* G = (T*)h->Gobj;
+    T* H = G + (size_t)k * k;
+    launch_gram<T>(W, n, k, (T*)h->gram_part, h->gchunks_w, G, st);                 // IEEE Gram products
+    launch_gram<T>((const T*)h->Tt, d, k, (T*)h->gram_part, h->gchunks_t, H, st);
+    launch_objective_identity<T>(G, H, k, acc, h->obj_out, st);
+    launch_norms<T>(W, n * k, h->obj_part, h->obj_out + 2, st);
+    launch_norms<T>(Tm, (int64_t)k * d, h->obj_part, h->obj_out + 4, st);
+    h->launches += 11;
+    CKL();
+    return 0;
+}
+
+extern "C" int rri_objective_contraction(rri_handle_t h, const void* W_dev, const void* T_dev, int32_t reuse_last_sweep,
+                                         double* out_host, void* stream)
+{
+    if (!h) return fail("null handle");
+    if (!h->X) return fail("rri_bind has not been called");
+    if (!W_dev || !T_dev || !out_host) return fail("null argument");
+    if (h->sparse || h->mk != MK_NONE) return fail("the objective through the contraction needs unmasked dense data");
+    if (!h->Cpart) return fail("no contraction workspace on this handle");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->world > 1 && h->p2p && h->order == RRI_ORDER_HALS && !(reuse_last_sweep && h->c2_valid))
+        return fail("with the peer exchange on, the objective through the contraction is available right after rri_sweeps");
+    int rc = h->dtype == RRI_F32 ? objective_contraction_impl<float>(h, (const float*)W_dev, (const float*)T_dev, reuse_last_sweep != 0, st)
+                                 : objective_contraction_impl<double>(h, (const double*)W_dev, (const double*)T_dev, reuse_last_sweep != 0, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out_host, h->obj_out, sizeof(double) * 6, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

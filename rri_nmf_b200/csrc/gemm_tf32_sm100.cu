@@ -16,10 +16,12 @@
 //     (whole factor slab for this K chunk) is shared by the MT row tiles a CTA works on at once, so the
 //     factor is re-read from L2 only once per MT*128 rows of A; A uses an evict-first L2 policy, B evict-last;
 //   * accumulators live in TMEM: two buffers of MT tiles x 128 lanes x NPAD fp32 columns.  The MMA warp
-//     alternates buffers every FLUSH K-chunks (1024 K); the 8 epilogue warps drain the finished buffer into
+//     alternates buffers every FLUSH K-chunks (4 x 32 = 128 K); the epilogue warps drain the finished buffer into
 //     fp32 registers while the next one fills.  Besides hiding the epilogue this bounds the length of any
-//     tensor-core accumulation chain: the MMA accumulator truncates, which over K = 100 000+ rows shows as a
-//     systematic -4e-4 relative bias (tools/tf32_probe.py); the register adds are round-to-nearest;
+//     tensor-core accumulation chain: the MMA accumulator truncates, which over K = 200 000 rows shows as a
+//     systematic -6.5e-4 relative bias without a flush, -6.5e-6 with a flush every 1024 K and -6e-7 every 128 K
+//     (profiles/r02_tf32_flush_sweep.txt; the shorter period costs 0.6 % of the sweep rate); the register adds are
+//     round-to-nearest;
 //   * stream-K work split: the (row super-tile, K chunk) units are divided evenly over the CTAs, so every
 //     SM streams the same number of bytes whatever M is (no wave quantisation at 157 or 196 tiles).
 //     A CTA whose segment covers a full K range writes C directly; first/last partial segments go to a
@@ -45,7 +47,7 @@ namespace {
 constexpr int BM = 128;            // rows per UMMA (M of the instruction, cta_group::1)
 constexpr int BK = 32;             // fp32 elements per 128-byte swizzle row
 constexpr int UK = 8;              // K of one tcgen05.mma kind::tf32
-constexpr int FLUSH = 32;           // K-chunks (x32 floats = 1024 K) accumulated in TMEM before a flush into registers
+constexpr int FLUSH = 4;            // K-chunks (x32 floats = 128 K) accumulated in TMEM before a flush into registers
 constexpr int A_TILE_BYTES = BM * BK * 4;      // 16 KB
 constexpr int SMEM_LIMIT = 227 * 1024;
 

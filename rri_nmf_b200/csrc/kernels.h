@@ -176,6 +176,18 @@ template <typename T>
 void launch_objective(const T* X, int64_t ldx, const void* M, int mk, int64_t ldm, const T* W,
                       const T* Tm, int64_t n, int64_t d, int k, double* part, int blocks, double* out,
                       cudaStream_t st);
+// pieces of the objective through the contraction (unmasked): ||X-WT||^2 = ||X||^2 - 2<X T', W> + <W'W, T T'>, fp64 sums
+//   out[0] = sum A[r,c]^2 (A rows x cols, leading dimension lda);   part: >= 8*sm_count doubles of scratch
+template <typename T>
+void launch_sumsq_rows(const T* A, int64_t rows, int64_t cols, int64_t lda, double* part, double* out, int sm_count,
+                       cudaStream_t st);
+//   out[0] = sum_e (sum_p C[p*stride + e]) * W[e]
+template <typename T>
+void launch_dot_parts(const T* C, int parts, int64_t stride, const T* W, int64_t len, double* part, double* out,
+                      int sm_count, cudaStream_t st);
+//   out[0] = 0.5 * (acc[0] - 2 acc[1] + sum G o H), out[1] = acc[0]
+template <typename T>
+void launch_objective_identity(const T* G, const T* H, int k, const double* acc, double* out, cudaStream_t st);
 // out[0] = sum v^2, out[1] = sum |v| over len contiguous elements (regulariser terms, nmf.py:72-75)
 template <typename T>
 void launch_norms(const T* v, int64_t len, double* part, double* out, cudaStream_t st);

@@ -378,8 +378,8 @@ sp_pass_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
 // stages block b of Q once and walks the sub-segments [ptr2[s][b], ptr2[s][b+1]) of its chunk c of the segments, a
 // warp per sub-segment, so every gather is a shared-memory read.  Per-block partial sums are written to
 // numer_part[b][s], denom_part[b][s] and added in block order by the solve kernel (deterministic).
-template <typename T, bool HASW, int U>
-__global__ void __launch_bounds__(1024, 1)
+template <typename T, bool HASW, int U, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restrict__ idx,
                        const uint16_t* __restrict__ idx16, T* __restrict__ E,
                        const T* __restrict__ wgt, const Quad<T>* __restrict__ Q, const T* __restrict__ own_po,
@@ -400,10 +400,23 @@ sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restri
     const bool apply = own_po != nullptr;
     const int32_t ibase = (int32_t)base;
     const int64_t pstride = (int64_t)nblk + 1;
-    for (int64_t s = s0 + warp; s < s1; s += nwarps) {
-        const int64_t beg = ptr2[s * pstride + b], end = ptr2[s * pstride + b + 1];
-        const T opo = apply ? own_po[s] : T(0), opn = apply ? own_pn[s] : T(0);
-        const T oc = own_cur[s];
+    // the bounds and the per-segment scalars of the NEXT sub-segment are requested before this one is streamed: the
+    // pointer load would otherwise sit in front of every sub-segment's first batch (two dependent round trips per ~3 KB)
+    int64_t s = s0 + warp;
+    int64_t beg = 0, end = 0;
+    T opo = T(0), opn = T(0), oc = T(0);
+    if (s < s1) {
+        beg = ptr2[s * pstride + b]; end = ptr2[s * pstride + b + 1];
+        opo = apply ? own_po[s] : T(0); opn = apply ? own_pn[s] : T(0); oc = own_cur[s];
+    }
+    while (s < s1) {
+        const int64_t sn = s + nwarps;
+        int64_t nbeg = 0, nend = 0;
+        T nopo = T(0), nopn = T(0), noc = T(0);
+        if (sn < s1) {
+            nbeg = ptr2[sn * pstride + b]; nend = ptr2[sn * pstride + b + 1];
+            nopo = apply ? own_po[sn] : T(0); nopn = apply ? own_pn[sn] : T(0); noc = own_cur[sn];
+        }
         T num = T(0), den = T(0);
         for (int64_t p0 = beg + lane; p0 < end + lane; p0 += 32 * U) {        // (p0 - lane) < end: uniform per warp
             int32_t q[U]; T ev[U]; T m[U];
@@ -429,6 +442,7 @@ sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restri
             denom_part[(int64_t)b * nseg + s] = den;
             if (b == 0) own_save[s] = oc;
         }
+        s = sn; beg = nbeg; end = nend; opo = nopo; opn = nopn; oc = noc;
     }
 }
 
@@ -454,7 +468,10 @@ __global__ void sp_subptr_kernel(const int64_t* __restrict__ ptr, const int32_t*
 // would leave its CTAs with a fraction of the work of the others).
 int sp_block_len(int elem_size, int64_t nother, int* nblk_out)
 {
-    const int64_t cap = (128 * 1024) / (4 * elem_size);
+    // RRI_SP_BLOCK_KB: shared-memory staging block (default 128 KB: one 1024-thread CTA per SM; <= 64 KB: two
+    // 512-thread CTAs per SM, shorter sub-segments)
+    static const int kb = [] { const char* e = getenv("RRI_SP_BLOCK_KB"); const int v = e ? atoi(e) : 128; return v >= 8 && v <= 128 ? v : 128; }();
+    const int64_t cap = ((int64_t)kb * 1024) / (4 * elem_size);
     const int64_t nblk = nother > 0 ? (nother + cap - 1) / cap : 1;
     int64_t nb = (nother + nblk - 1) / nblk;
     nb = (nb + 31) / 32 * 32;
@@ -497,7 +514,19 @@ int launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* 
         if (chunks < 1) chunks = 1;
         if ((int64_t)chunks * 32 > s.nseg) chunks = (int)((s.nseg + 31) / 32);
         if (chunks < 1) chunks = 1;
-        auto kern = w ? sp_pass_blocked_kernel<T, true, U> : sp_pass_blocked_kernel<T, false, U>;
+        if (smem <= 64 * 1024) {
+            // two CTAs of 512 threads per SM: one CTA's staging phase overlaps the other's streaming
+            chunks = 2 * sm_count / s.nblk;
+            if (chunks < 1) chunks = 1;
+            if ((int64_t)chunks * 16 > s.nseg) chunks = (int)((s.nseg + 15) / 16);
+            if (chunks < 1) chunks = 1;
+            auto kern = w ? sp_pass_blocked_kernel<T, true, U, 512, 2> : sp_pass_blocked_kernel<T, false, U, 512, 2>;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            kern<<<(unsigned)(s.nblk * chunks), 512, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save,
+                                                                numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks);
+            return s.nblk;
+        }
+        auto kern = w ? sp_pass_blocked_kernel<T, true, U, 1024, 1> : sp_pass_blocked_kernel<T, false, U, 1024, 1>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
         kern<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save, numer,
                                                              denom, s.nseg, s.nblk, s.nb, s.nother, chunks);

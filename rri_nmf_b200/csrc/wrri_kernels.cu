@@ -439,7 +439,118 @@ void launch_norms(const T* v, int64_t len, double* part, double* out, cudaStream
     norms_finalize_kernel<<<1, 32, 0, st>>>(part, blocks, out);
 }
 
+// ------------------------------------------------------------------------------------------------
+// objective through the contraction (unmasked data):  ||X - W T||^2 = ||X||^2 - 2 <X T', W> + <W'W, T T'>
+// The contraction X T' is the W half-step's own (still in its buffer after a block-order sweep), so an objective per
+// sweep costs two Gram products and a dot product instead of a pass over X.  All sums in fp64.
+// ------------------------------------------------------------------------------------------------
+// out[0] = sum over rows r < rows, columns c < cols of A[r*lda + c]^2
+template <typename T>
+__global__ void __launch_bounds__(256)
+sumsq_rows_kernel(const T* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, double* __restrict__ part)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const double x = (double)ld_stream(A + r * lda + c);
+        s += x * x;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+// part[b] = partial of sum_e (sum_p C[p*stride + e]) * W[e]
+template <typename T>
+__global__ void __launch_bounds__(256)
+dot_parts_kernel(const T* __restrict__ C, int parts, int64_t stride, const T* __restrict__ W, int64_t len,
+                 double* __restrict__ part)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        double c = 0.0;
+        for (int p = 0; p < parts; ++p) c += (double)C[(int64_t)p * stride + i];
+        s += c * (double)W[i];
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out)
+{
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < blocks; ++b) s += part[b];
+        out[0] = s;
+    }
+}
+
+template <typename T>
+void launch_sumsq_rows(const T* A, int64_t rows, int64_t cols, int64_t lda, double* part, double* out, int sm_count,
+                       cudaStream_t st)
+{
+    int64_t blocks = (rows * cols + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 8 * sm_count) blocks = 8 * sm_count;
+    if (blocks < 1) blocks = 1;
+    sumsq_rows_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(A, rows, cols, lda, part);
+    sum_partials_kernel<<<1, 32, 0, st>>>(part, (int)blocks, out);
+}
+
+template <typename T>
+void launch_dot_parts(const T* C, int parts, int64_t stride, const T* W, int64_t len, double* part, double* out,
+                      int sm_count, cudaStream_t st)
+{
+    int64_t blocks = (len + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 8 * sm_count) blocks = 8 * sm_count;
+    if (blocks < 1) blocks = 1;
+    dot_parts_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(C, parts, stride, W, len, part);
+    sum_partials_kernel<<<1, 32, 0, st>>>(part, (int)blocks, out);
+}
+
+// out[0] = 0.5 * (xsq - 2 cross + sum_ab G[a,b] H[a,b]),  out[1] = xsq      (acc = {xsq, cross})
+template <typename T>
+__global__ void __launch_bounds__(256)
+objective_identity_kernel(const T* __restrict__ G, const T* __restrict__ H, int kk, const double* __restrict__ acc,
+                          double* __restrict__ out)
+{
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int e = threadIdx.x; e < kk; e += blockDim.x) s += (double)G[e] * (double)H[e];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double q = 0.0;
+        for (int w = 0; w < 8; ++w) q += red[w];
+        out[0] = 0.5 * (acc[0] - 2.0 * acc[1] + q);
+        out[1] = acc[0];
+    }
+}
+
+template <typename T>
+void launch_objective_identity(const T* G, const T* H, int k, const double* acc, double* out, cudaStream_t st)
+{
+    objective_identity_kernel<T><<<1, 256, 0, st>>>(G, H, k * k, acc, out);
+}
+
 #define RRI_INST(T)                                                                                         \
+    template void launch_sumsq_rows<T>(const T*, int64_t, int64_t, int64_t, double*, double*, int, cudaStream_t); \
+    template void launch_dot_parts<T>(const T*, int, int64_t, const T*, int64_t, double*, double*, int, cudaStream_t); \
+    template void launch_objective_identity<T>(const T*, const T*, int, const double*, double*, cudaStream_t); \
     template void launch_wrri_tstats<T>(const T*, int64_t, const void*, int, int64_t, const T*, const T*,   \
                                         int64_t, int64_t, int, int, T*, T*, const TilePlan&, cudaStream_t); \
     template void launch_wrri_wstats<T>(const T*, int64_t, const void*, int, int64_t, const T*, const T*,   \

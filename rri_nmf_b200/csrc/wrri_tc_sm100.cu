@@ -340,22 +340,23 @@ __device__ __forceinline__ void epi_barrier_tma()
     asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS_TMA * 32) : "memory");
 }
 
-// 16 consecutive fp32 of row `row` starting at tile column c0 (multiple of 16) from a tile stored as two
-// [128 rows x 128 bytes] boxes with the 128-byte swizzle (16-byte chunk index XOR (row & 7))
-__device__ __forceinline__ void lds_row16_swz(const uint8_t* tile, int row, int c0, float v[16])
+__device__ __forceinline__ float4 lds128(uint32_t saddr)
 {
-    const uint8_t* base = tile + (c0 >> 5) * X_BOX_BYTES + row * 128;
-    const int ch0 = (c0 & 31) >> 2;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4 x = *reinterpret_cast<const float4*>(base + (((ch0 + j) ^ (row & 7)) << 4));
-        v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-    }
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
 }
-// byte b (0..255) as a float without the conversion pipe: 0x4B000000 | b is 8388608 + b
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+// byte i of w (0..255) as a float without the conversion pipe: one PRMT builds the bits of 8388608 + b, one FADD
+// removes the offset
 __device__ __forceinline__ float byte_to_float(uint32_t w, int i)
 {
-    return __uint_as_float(0x4B000000u | ((w >> (8 * i)) & 0xffu)) - 8388608.0f;
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440u | (uint32_t)i)) - 8388608.0f;
 }
 
 template <int MODE, int MK>
@@ -485,16 +486,23 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         const int c0 = 16 * cgp;
         const int NS = p.xm_stages;
         const float* Trow = p.Tt;                // T[t, :] (contiguous), W[:, t] = Wp[:, t] (stride KP)
-
-        // MODE 0: per-column accumulators (this thread's row only) kept over all row tiles; MODE 1: one per row
-        float nacc[MODE == 0 ? 16 : 1], dacc[MODE == 0 ? 16 : 1];
+        // shared-memory addresses of this thread's 4 x 16 bytes of an X (or fp32 weight) tile: box (c0 >> 5), row, and
+        // the 16-byte chunks (c0 & 31)/4 + j with the 128-byte swizzle (chunk index XOR (row & 7)); loop invariant
+        const uint32_t xrow = smem_u32(sm_xm) + (uint32_t)((c0 >> 5) * X_BOX_BYTES + row * 128);
+        uint32_t xoff[4];
 #pragma unroll
-        for (int i = 0; i < (MODE == 0 ? 16 : 1); ++i) { nacc[i] = 0.f; dacc[i] = 0.f; }
+        for (int j = 0; j < 4; ++j) xoff[j] = (uint32_t)(((((c0 & 31) >> 2) + j) ^ (row & 7)) << 4);
+        const uint32_t mrow = smem_u32(sm_xm) + (uint32_t)(X_TILE_BYTES + row * TN + c0);      // byte mask: 16 bytes
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
 
-        // factor entries of topic t for this thread's columns / row.  The fixed side is loaded once; the side that
-        // changes with the tile is requested one tile ahead.
-        float tt[16];
-        float wt = 0.f;
+        // With u = X - WT (the full residual) the statistics of nmf.py:687-701 / :735-746 are
+        //   T-step: numer[c] = sum_r w_r m (u + w_r t_c) = A[c] + t_c D[c],  A[c] = sum_r (m w_r) u,  D[c] = sum_r (m w_r) w_r
+        //   W-step: numer[r] = sum_c t_c m (u + w_r t_c) = A[r] + w_r D[r],  A[r] = sum_c (m t_c) u,  D[r] = sum_c (m t_c) t_c
+        // i.e. four operations per element; the add-back of topic t happens once per CTA instead of once per element.
+        float A[MODE == 0 ? 16 : 1], D[MODE == 0 ? 16 : 1];
+#pragma unroll
+        for (int i = 0; i < (MODE == 0 ? 16 : 1); ++i) { A[i] = 0.f; D[i] = 0.f; }
+
         auto load_tt = [&](int ctile, float out[16]) {
             const int64_t gc = (int64_t)ctile * TN + c0;
 #pragma unroll
@@ -508,63 +516,88 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             const int64_t gi = (int64_t)rt * TM + row;
             return gi < p.n ? __ldg(p.Wp + gi * p.KP + p.t) : 0.f;
         };
-        float ttn[MODE == 1 ? 16 : 1];
-        float wtn = 0.f;
-        if (MODE == 0) { load_tt(fixed_tile, tt); wt = ntiles > 0 ? load_wt(vb) : 0.f; }
-        else { wt = load_wt(fixed_tile); if (ntiles > 0) load_tt(vb, tt); }
-
+        // the factor entries that change with the tile (MODE 0: w_r, MODE 1: t_c) are requested one tile ahead
+        float fac[MODE == 0 ? 1 : 16], facn[MODE == 0 ? 1 : 16];
+        if (ntiles > 0) {
+            if (MODE == 0) fac[0] = load_wt(vb); else load_tt(vb, fac);
+        }
+        int s = 0;
+        uint32_t xph = 0;
         for (int n = 0; n < ntiles; ++n) {
-            const int a = n & 1, s = n % NS;
+            const int a = n & 1;
             if (n + 1 < ntiles) {
-                if (MODE == 0) wtn = load_wt(vb + n + 1);
-                else load_tt(vb + n + 1, ttn);
+                if (MODE == 0) facn[0] = load_wt(vb + n + 1); else load_tt(vb + n + 1, facn);
             }
             // ---- this warp's 32 x 16 block of the product: TMEM -> registers
             mbar_wait(&acc_full[a], (n >> 1) & 1);
             tc_fence_after();
             uint32_t dr[16];
-            tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TN + c0), dr);
+            tmem_ld16_issue(tacc + (uint32_t)(a * TN), dr);
             // ---- the same block of X and of the mask from the stage
-            mbar_wait(&xm_full[s], (n / NS) & 1);
-            const uint8_t* stage = sm_xm + (size_t)s * XM_STAGE;
+            mbar_wait(&xm_full[s], xph);
+            const uint32_t so = (uint32_t)s * XM_STAGE;
             float x[16], m[16];
-            lds_row16_swz(stage, row, c0, x);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = lds128(xrow + so + xoff[j]);
+                x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+            }
             if (MK == MK_U8) {
-                const uint4 mw = *reinterpret_cast<const uint4*>(stage + X_TILE_BYTES + row * TN + c0);
+                const uint4 mw = lds128u(mrow + so);
                 const uint32_t w4[4] = {mw.x, mw.y, mw.z, mw.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int v = 0; v < 4; ++v) m[4 * j + v] = byte_to_float(w4[j], v);
             } else {
-                lds_row16_swz(stage + X_TILE_BYTES, row, c0, m);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = lds128(xrow + (uint32_t)X_TILE_BYTES + so + xoff[j]);
+                    m[4 * j] = v.x; m[4 * j + 1] = v.y; m[4 * j + 2] = v.z; m[4 * j + 3] = v.w;
+                }
             }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_free[a]);                 // the accumulator block is in registers
-            // ---- element-wise statistics: M o (X - W_{t->0} T) with topic t added back in fp32
-            const float ww = wt * wt;
-            float nrow = 0.f, drow = 0.f;
+            if (lane == 0) mbar_arrive(&acc_free[a]);                  // the accumulator block is in registers
+            // ---- element-wise statistics
+            if (MODE == 0) {
+                const float wr = fac[0];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                const float res = m[c] * (x[c] - __uint_as_float(dr[c]) + wt * tt[c]);
-                if (MODE == 0) {
-                    nacc[c] = fmaf(wt, res, nacc[c]);
-                    dacc[c] = fmaf(ww, m[c], dacc[c]);
-                } else {
-                    nrow = fmaf(res, tt[c], nrow);
-                    drow = fmaf(m[c] * tt[c], tt[c], drow);
+                for (int c = 0; c < 16; ++c) {
+                    const float v = m[c] * wr;
+                    A[c] = fmaf(v, x[c] - __uint_as_float(dr[c]), A[c]);
+                    D[c] = fmaf(v, wr, D[c]);
                 }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&xm_free[s]);                  // every lane has consumed its X / mask values
-            if (MODE == 1) { nacc[0] += nrow; dacc[0] += drow; }
-            if (MODE == 0) wt = wtn;
-            else {
+                fac[0] = facn[0];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xm_free[s]);               // every lane has consumed its X / mask values
+            } else {
+                float a0 = 0.f, d0 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 16; ++c) tt[c] = ttn[c];
+                for (int c = 0; c < 16; ++c) {
+                    const float v = m[c] * fac[c];
+                    a0 = fmaf(v, x[c] - __uint_as_float(dr[c]), a0);
+                    d0 = fmaf(v, fac[c], d0);
+                }
+                A[0] += a0; D[0] += d0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xm_free[s]);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) fac[c] = facn[c];
             }
+            if (++s == NS) { s = 0; xph ^= 1u; }
+        }
+        // add topic t back (once per CTA): numer = A + (own factor entry) * D
+        float nacc[MODE == 0 ? 16 : 1], dacc[MODE == 0 ? 16 : 1];
+        if (MODE == 0) {
+            float tt[16];
+            load_tt(fixed_tile, tt);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { nacc[c] = fmaf(tt[c], D[c], A[c]); dacc[c] = D[c]; }
+        } else {
+            nacc[0] = fmaf(load_wt(fixed_tile), D[0], A[0]);
+            dacc[0] = D[0];
         }
 
         // ---- once per CTA: cross-warp reduction through the (now idle) stage buffers, fixed order

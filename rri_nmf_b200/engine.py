@@ -209,13 +209,14 @@ class RRIEngine(object):
 
     @staticmethod
     def params(reg_w_l1=0.0, reg_w_l2=0.0, reg_t_l1=0.0, reg_t_l2=0.0, ub_w=None, ub_t=None,
-               fix_W=False, fix_T=False, simplex_T=False, eps=EPS_DIV_BY_ZERO):
+               fix_W=False, fix_T=False, simplex_T=False, eps=EPS_DIV_BY_ZERO, sp_refresh_every=1):
         p = RriParams()
         p.reg_w_l1, p.reg_w_l2, p.reg_t_l1, p.reg_t_l2 = float(reg_w_l1), float(reg_w_l2), float(reg_t_l1), float(reg_t_l2)
         p.ub_w = float(ub_w) if ub_w else 0.0
         p.ub_t = float(ub_t) if ub_t else 0.0
         p.eps = float(eps)
         p.fix_W, p.fix_T, p.simplex_T = int(bool(fix_W)), int(bool(fix_T)), int(bool(simplex_T))
+        p.sp_refresh_every = int(sp_refresh_every)
         return p
 
     def _check_factors(self, W, T):
@@ -246,12 +247,18 @@ class RRIEngine(object):
         check(self.lib.rri_topic_sums(self.h, sT, sW, self._stream()))
         return np.array(sT[:]), np.array(sW[:])
 
-    def objective_terms(self, W, T):
+    def objective_terms(self, W, T, via_contraction=False, reuse_last_sweep=False):
         """[0.5*sum M(X-WT)^2, sum M X^2, sum W^2, sum |W|, sum T^2, sum |T|]; the first four are
-        all-reduced over the row shards when a communicator is attached."""
+        all-reduced over the row shards when a communicator is attached.
+        via_contraction (unmasked dense data): ||X||^2 - 2<X T', W> + <W'W, T T'> instead of an explicit pass over X;
+        reuse_last_sweep: W, T are exactly what the last block-order `sweeps` call left (its contraction is reused)."""
         self._check_factors(W, T)
         out = (C.c_double * 6)()
-        check(self.lib.rri_objective(self.h, _ptr(W), _ptr(T), out, self._stream()))
+        if via_contraction:
+            check(self.lib.rri_objective_contraction(self.h, _ptr(W), _ptr(T), int(bool(reuse_last_sweep)), out,
+                                                     self._stream()))
+        else:
+            check(self.lib.rri_objective(self.h, _ptr(W), _ptr(T), out, self._stream()))
         v = np.array(out[:])
         if self.comm is not None and self.comm.world > 1:
             import torch.distributed as dist
@@ -260,9 +267,10 @@ class RRIEngine(object):
             v[:4] = t.cpu().numpy()
         return v
 
-    def objective(self, W, T, reg_w_l1=0.0, reg_w_l2=0.0, reg_t_l1=0.0, reg_t_l2=0.0):
+    def objective(self, W, T, reg_w_l1=0.0, reg_w_l2=0.0, reg_t_l1=0.0, reg_t_l2=0.0, via_contraction=False,
+                  reuse_last_sweep=False):
         """nmf.py:71-94"""
-        v = self.objective_terms(W, T)
+        v = self.objective_terms(W, T, via_contraction, reuse_last_sweep)
         return float(v[0] + 0.5 * reg_w_l2 * v[2] + 0.5 * reg_t_l2 * v[4] + reg_t_l1 * v[5] + reg_w_l1 * v[3])
 
     def rel_error(self, W, T):

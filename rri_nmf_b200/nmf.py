@@ -9,6 +9,18 @@ Additional keyword-only arguments select the device path:
                   'hals' -- block order: all T-steps then all W-steps (2 passes over X per sweep)
     math          'ieee' (default) or 'tf32' (tcgen05 tensor-core contractions; float32 + 'hals')
     comm          engine.NcclComm for a row-sharded multi-GPU run (X, W_in, W_mat are the local shards)
+    objective     how `obj_history` is evaluated: 'exact' = an explicit pass over X per evaluation (the reference's
+                  TrueObjComputer, nmf.py:71-94); 'contraction' = ||X||^2 - 2<X T', W> + <W'W, T T'> from the block-order
+                  sweep's own contraction (no extra pass over X; unmasked dense data, update_order='hals'); 'auto'
+                  (default) = 'contraction' where it applies with IEEE arithmetic (fp64 / math='ieee'), else 'exact'.
+                  With math='tf32' the contraction form carries the TF32 rounding of <X T', W> amplified by
+                  ||X||^2 / ||X - WT||^2 (~1e-3 relative at a 3 % residual): ask for it explicitly.
+    sparse_refresh_every  observed-entries (sparse X) engines, interleaved order: rebuild the maintained residual from the
+                  factors every this many sweeps of one engine call (default 1: every sweep, bitwise re-entrant; larger
+                  values skip 17 % of a sweep at config-4 shape and let fp rounding of the rank-one updates accumulate
+                  over that many sweeps)
+    return_reconstruction_err  also return 'reconstruction_err' = ||M^(1/2) o (X - W T)||_F of the returned factors,
+                  evaluated on the device before the engine is released (the estimators' `reconstruction_err_`)
     init_on_device  where the NNDSVD initialisation runs when W_in/T_in are not both given: True = on the GPU that
                   holds X (`_device_init.py`; X never returns to the host), False = on the host (`_host.py`, NumPy /
                   sklearn, as the reference does), None (default) = on the device when X is already a CUDA tensor or
@@ -35,15 +47,59 @@ eps_div_by_zero = EPS_DIV_BY_ZERO          # nmf.py:52
 
 
 class DeviceObjective(object):
-    """Stand-in for the reference's TrueObjComputer (nmf.py:58-94) returned as 'obj_calculator'."""
+    """Stand-in for the reference's TrueObjComputer (nmf.py:58-94) returned as 'obj_calculator'.
 
-    def __init__(self, engine, W, T, regs):
+    While nmf() runs it evaluates the objective on the live engine.  When nmf() returns, the engine (and with it the
+    device copy of X, the mask and the workspace) is released: the calculator keeps the value of the last
+    evaluation and references to the caller's X / W_mat and the returned factors, and `true_objective()` rebuilds a
+    short-lived engine on demand -- like the reference's object, which holds plain arrays.  Picklable."""
+
+    def __init__(self, engine, W, T, regs, via_contraction=False):
         self.engine, self.W, self.T, self.regs = engine, W, T, regs
         self.obj = np.inf
+        self._rebuild = None
+        self.via_contraction = via_contraction      # unmasked block order: objective from the sweep's own contraction
+        self._after_sweep = False                   # set by nmf() for the evaluation that directly follows a sweep
 
     def true_objective(self):
-        self.obj = self.engine.objective(self.W, self.T, **self.regs)
+        if self.engine is not None:
+            self.obj = self.engine.objective(self.W, self.T, via_contraction=self.via_contraction,
+                                             reuse_last_sweep=self._after_sweep, **self.regs)
+            self._after_sweep = False
+        elif self._rebuild is not None:
+            X, W_mat, device, dtype, order = self._rebuild
+            device = torch.device(device)
+            with torch.cuda.device(device):
+                if _is_sparse(X):
+                    Xd, Md = _sparse_to_device(X, W_mat, device, dtype)
+                else:
+                    Xd, Md = _to_device(X, device, dtype), _mask_to_device(W_mat, device, dtype)
+                eng = RRIEngine(Xd, int(np.shape(self.W)[1]), W_mat=Md, order='rri')
+                try:
+                    self.obj = eng.objective(_to_device(self.W, device, dtype).contiguous(),
+                                             _to_device(self.T, device, dtype).contiguous(), **self.regs)
+                finally:
+                    eng.close()
         return self.obj
+
+    def _detach(self, X, W_mat, W, T, device, dtype, order):
+        """called by nmf() before it closes the engine"""
+        self.engine = None
+        self.W, self.T = W, T
+        self._rebuild = (X, W_mat, str(device), dtype, order)
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st['engine'] = None
+        return st
+
+
+def _mask_to_device(W_mat, device, dtype):
+    if W_mat is None:
+        return None
+    if isinstance(W_mat, torch.Tensor) and W_mat.dtype in (torch.uint8, torch.bool):
+        return W_mat.to(device)
+    return _to_device(W_mat, device, dtype)
 
 
 def _universal_stopping_condition(obj_history, eps_stop=1e-4):
@@ -145,8 +201,8 @@ def _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum
 
 
 _STAGE = {'bufs': None, 'bytes': 0}
-_STAGE_CHUNK_BYTES = 32 << 20
-_STAGE_THREADS = 8
+_STAGE_CHUNK_BYTES = 8 << 20     # measured on the B200 hosts (profiles/r02_h2d_staging_probe.txt): 4 threads x 8 MB
+_STAGE_THREADS = 4               # chunks reach the pinned copy rate (53 vs 54 GB/s); torch's pageable .to(): 11 GB/s
 
 
 def _stage_buffers(nbuf, nbytes):
@@ -228,7 +284,7 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         n_resets=23, reg_w_l2=0, reg_t_l2=0, reg_w_l1=0, reg_t_l1=0, diagnostics=[], store_gradients=False,
         ind_rows_to_store=None, eps_gauss_t=None, delta_gauss_t=None,
         *, device=None, update_order='rri', math='ieee', comm=None, engine=None, sweeps_per_call=16,
-        init_on_device=None):
+        init_on_device=None, return_reconstruction_err=False, sparse_refresh_every=1, objective='auto'):
     """Non-negative factorisation X ~ W T by rank-one residue iteration.  See the reference docstring
     (nmf.py:109-269) for the arguments; returns {'W', 'T', 'iter_cputime', 'random_state'[, 'obj_history',
     'obj_calculator', 'diagnostics']} (nmf.py:551-560).  W and T come back as the kind of array X was
@@ -351,6 +407,7 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         T0 = T_in
     timing = {}
     _t0 = time.perf_counter()
+    a_W_mat_user = W_mat
     with torch.cuda.device(device):
         if sparse_in:
             Xd, W_mat = _sparse_to_device(X, W_mat, device, dtype)
@@ -372,14 +429,8 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
             W = W.clone()
         if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
             T = T.clone()
-        Md = None
-        if sparse_in:
-            Md = W_mat                          # 1-D entry weights (or None), already on the device
-        elif W_mat is not None:
-            if isinstance(W_mat, torch.Tensor) and W_mat.dtype in (torch.uint8, torch.bool):
-                Md = W_mat.to(device)
-            else:
-                Md = _to_device(W_mat, device, dtype)
+        W_mat_user = a_W_mat_user
+        Md = W_mat if sparse_in else _mask_to_device(W_mat, device, dtype)   # sparse: 1-D entry weights, already there
 
         # (no synchronisation here: the pinned host -> device copy of X keeps running while the engine allocates
         # its workspace; the first kernel is stream-ordered behind it)
@@ -389,16 +440,21 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
         if engine is None:
             engine = RRIEngine(Xd, k, W_mat=Md, order=update_order, math=math, comm=comm)
         timing['engine_setup_s'] = time.perf_counter() - _t1       # workspace, transposed copy of X, peer mapping
-        keep = False
         try:
             _t2 = time.perf_counter()
             out = _solve(engine, X if sparse_in else Xd, W, T, rtv, locals())
             timing['solve_s'] = time.perf_counter() - _t2           # (rest of the H2D copy,) sweeps, device -> host copy of W, T
             out['timing'] = timing
-            keep = 'obj_calculator' in out        # the returned objective calculator owns the engine
+            if return_reconstruction_err:
+                Wd = W if isinstance(out['W'], np.ndarray) else out['W']
+                Td = T if isinstance(out['T'], np.ndarray) else out['T']
+                out['reconstruction_err'] = float(np.sqrt(2.0 * engine.objective_terms(Wd, Td)[0]))
+            if 'obj_calculator' in out and own_engine:
+                # the calculator outlives this call without pinning device memory (and stays picklable)
+                out['obj_calculator']._detach(X, W_mat_user, out['W'], out['T'], device, dtype, update_order)
             return out
         finally:
-            if own_engine and not keep:
+            if own_engine:
                 _t3 = time.perf_counter()
                 engine.close()
                 timing['teardown_s'] = time.perf_counter() - _t3
@@ -423,24 +479,43 @@ def _solve(engine, Xd, W, T, rtv, a):
         engine.project_rows_simplex(T, t_row_sum)
 
     params = engine.params(ub_w=w_row_sum, ub_t=t_row_sum, fix_T=fix_T,
-                           simplex_T=bool(project_T_each_iter and t_row_sum and not fix_T), **regs)
+                           simplex_T=bool(project_T_each_iter and t_row_sum and not fix_T),
+                           sp_refresh_every=a['sparse_refresh_every'], **regs)
     masked = engine.masked
 
     def host_view(t):
         return t.detach().cpu().numpy() if numpy_io else t
 
+    # User callbacks (early_stop, diagnostics) get what the reference gives them: arrays of the kind X was.  A callback
+    # carrying the attribute `device_tensors = True` (the recommender estimator's validation RMSE) is handed the
+    # device-resident X, W, T instead -- nothing returns to the host between sweeps.
+    cbs = ([early_stop] if callable(early_stop) else []) + list(diagnostics)
+    need_host = any(not getattr(f, 'device_tensors', False) for f in cbs)
     Xcb = None
-    if callable(early_stop) or diagnostics:
+    if cbs and need_host:
         Xcb = Xd if a['sparse_in'] else host_view(Xd)          # sparse input is handed to callbacks as given
+
+    def call_cb(f):
+        if getattr(f, 'device_tensors', False):
+            return f(Xd, W, T)
+        return f(Xcb, host_view(W), host_view(T))
+
     state = {'n_resets_remaining': a['n_resets']}
     iter_cputime = []
     obj_history = []
-    OBJ = DeviceObjective(engine, W, T, regs) if compute_obj_each_iter else None
+    obj_mode = a['objective']
+    if obj_mode not in ('auto', 'exact', 'contraction'):
+        raise ValueError("objective must be 'auto', 'exact' or 'contraction'")
+    can_contract = engine.order == 'hals' and not masked and not fix_T
+    if obj_mode == 'contraction' and not can_contract:
+        raise ValueError("objective='contraction' needs unmasked dense data and update_order='hals'")
+    via_contraction = can_contract and (obj_mode == 'contraction' or (obj_mode == 'auto' and engine.math == 'ieee'))
+    OBJ = DeviceObjective(engine, W, T, regs, via_contraction) if compute_obj_each_iter else None
     if early_stop:
         last_score = np.inf
         W_prev, T_prev = W.clone(), T.clone()
     for f in diagnostics:
-        rtv['diagnostics'][f.__name__].append(f(Xcb, host_view(W), host_view(T)))
+        rtv['diagnostics'][f.__name__].append(call_cb(f))
 
     # sweeps can be batched into one library call when nothing on the host has to look at the state
     # in between (N sweeps in one call == N calls of one sweep, bit for bit)
@@ -463,7 +538,7 @@ def _solve(engine, Xd, W, T, rtv, a):
             if callable(early_stop):
                 # row shards: every rank scores its own rows; the decision uses the mean over ranks so that all
                 # ranks revert and leave together
-                this_score = _all_mean(comm, early_stop(Xcb, host_view(W), host_view(T)))
+                this_score = _all_mean(comm, call_cb(early_stop))
             else:
                 this_score = obj_history[-1] if (compute_obj_each_iter and obj_history) else np.inf
             if this_score > last_score:
@@ -499,11 +574,13 @@ def _solve(engine, Xd, W, T, rtv, a):
         if project_W_each_iter and not a['fix_W'] and w_row_sum is not None:      # nmf.py:481-484
             engine.project_rows_simplex(W, w_row_sum)
         if compute_obj_each_iter:                                                  # nmf.py:488-489
+            # (the sweep's own contraction is still valid unless W was projected after it)
+            OBJ._after_sweep = not (project_W_each_iter and w_row_sum is not None) and not a['fix_W']
             obj_history.append(OBJ.true_objective())
         now = time.process_time()
         iter_cputime.extend([now] * ns)
         for f in diagnostics:                                                      # nmf.py:495-500
-            rtv['diagnostics'][f.__name__].append(f(Xcb, host_view(W), host_view(T)))
+            rtv['diagnostics'][f.__name__].append(call_cb(f))
         # stop decisions are collective on row shards (a rank that left alone would hang the others' exchange)
         if _all_any(comm, time.time() - t_global_start >= max_time):              # nmf.py:506-508
             break

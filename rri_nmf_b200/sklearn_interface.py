@@ -101,11 +101,13 @@ class NMF_TM_Estimator(_FactorMixin, sklearn.base.BaseEstimator, sklearn.base.Tr
         soln = nmf(X, self.k, max_iter=max_iter, max_time=max_time, project_W_each_iter=False, w_row_sum=1.0,
                    project_T_each_iter=True, t_row_sum=1.0, do_final_project_W=self.do_final_project_W,
                    W_in=W_in, T_in=T_in, reg_w_l1=self.wr1, reg_w_l2=self.wr2, reg_t_l1=self.tr1,
-                   reg_t_l2=self.tr2, random_state=self.random_state, **kw)
+                   reg_t_l2=self.tr2, random_state=self.random_state, return_reconstruction_err=True, **kw)
         self.W = soln.pop('W')
         self.T = soln.pop('T')
+        # ||X - W T||_F of the returned factors, evaluated by the engine on the device copy of X before it was
+        # released (no n x d host temporary, no host GEMM)
+        self._reconstruction_err = soln.pop('reconstruction_err')
         self.nmf_outputs = soln
-        self._reconstruction_err = float(np.linalg.norm(X - self.W.dot(self.T)))
         return self
 
     def fit_transform(self, X, y=None):
@@ -183,18 +185,24 @@ class NMF_RS_Estimator(_FactorMixin, sklearn.base.BaseEstimator):
             held = np.asarray(Xv[Iv, Jv]).ravel()
             lo, hi = float(self.min_rating), float(self.max_rating)
 
+            held_dev = {}
+
             def RMSE_val(Xign, W, T):
                 # validation RMSE over the held-out entries only, with the rating clip of
-                # sklearn_interface.py:85-91; evaluated where W and T live (device tensors or arrays)
+                # sklearn_interface.py:85-91; evaluated where W and T live.  nmf() hands this callback the device
+                # tensors (`device_tensors`): W, T and X never return to the host between sweeps, and the held-out
+                # triples are uploaded once.
                 if isinstance(W, torch.Tensor):
-                    ii = torch.as_tensor(Iv, device=W.device)
-                    jj = torch.as_tensor(Jv, device=W.device)
+                    if W.device not in held_dev:
+                        held_dev[W.device] = (torch.as_tensor(Iv, device=W.device), torch.as_tensor(Jv, device=W.device),
+                                              torch.as_tensor(held, device=W.device, dtype=W.dtype))
+                    ii, jj, ref = held_dev[W.device]
                     pred = (W[ii, :] * T[:, jj].t()).sum(1).clamp(lo, hi)
-                    ref = torch.as_tensor(held, device=W.device, dtype=pred.dtype)
                     return float(torch.sqrt(torch.mean((pred - ref) ** 2)))
                 pred = np.clip(np.einsum('ik,ki->i', W[Iv, :], T[:, Jv]), lo, hi)
                 return float(np.sqrt(np.mean((pred - held) ** 2)))
 
+            RMSE_val.device_tensors = True
             self.early_stop = RMSE_val
         else:
             self.early_stop = False
@@ -211,14 +219,13 @@ class NMF_RS_Estimator(_FactorMixin, sklearn.base.BaseEstimator):
                    reset_topic_method=None, early_stop=self.early_stop, project_T_each_iter=False,
                    t_row_sum=1.0, project_W_each_iter=False, w_row_sum=None,
                    W_mat=W_mat_tr, W_in=W_in, T_in=T_in, reg_w_l1=self.wr1,
-                   reg_t_l1=self.tr1, random_state=self.random_state, **kw)   # sklearn_interface.py:116-123
+                   reg_t_l1=self.tr1, random_state=self.random_state, return_reconstruction_err=True,
+                   **kw)   # sklearn_interface.py:116-123
         self.W = soln.pop('W')
         self.T = soln.pop('T')
+        self._reconstruction_err = soln.pop('reconstruction_err')     # over the observed training entries, on device
         self.nmf_outputs = soln
         self.Xpred = _EMPTY
-        I, J = Xtr.nonzero()
-        pred = np.einsum('ik,ki->i', self.W[I, :], self.T[:, J])
-        self._reconstruction_err = float(np.sqrt(((pred - np.asarray(Xtr[I, J]).ravel()) ** 2).sum()))
         return self
 
     def fit_from_Xtr(self, Xtr):

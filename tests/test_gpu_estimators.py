@@ -27,12 +27,50 @@ def test_convergence_RS_Estimator(R):
     assert Wn.shape == (n, 5) and np.all(Wn >= 0)
 
 
+@pytest.mark.parametrize('sparse', [False, True])
+def test_RS_Estimator_early_stop_on_device_matches_reference(R, sparse):
+    """the estimator's validation-RMSE early stop (sklearn_interface.py:85-93, nmf.py:381-407) runs on
+    device tensors -- W, T and X do not return to the host between sweeps -- and stops where the unmodified
+    reference stops on the same fixture (golden rs_estimator_f64.npz: 3 sweeps run, the third reverted)."""
+    import torch
+    g = golden('rs_estimator_f64.npz')
+    X = golden('recsys_wrri_f64.npz')['X']
+    n, d = X.shape
+    big_d2h = []
+    orig_cpu = torch.Tensor.cpu
+
+    def counting_cpu(self, *a, **kw):
+        if self.is_cuda and self.numel() >= min(n, d) * 5:
+            big_d2h.append(tuple(self.shape))
+        return orig_cpu(self, *a, **kw)
+
+    torch.Tensor.cpu = counting_cpu
+    try:
+        E = R.NMF_RS_Estimator(n, d, 5, random_state=0, max_iter=20, sparse=sparse).fit_from_Xtr(X)
+    finally:
+        torch.Tensor.cpu = orig_cpu
+    # exactly one device -> host copy of each factor (the returned W and T); X and the per-sweep states stay put
+    assert sorted(big_d2h) == sorted([(n, 5), (5, d)]), big_d2h
+    oh = np.array(E.nmf_outputs['obj_history'])
+    assert oh.shape == g['obj_history'].shape and np.allclose(oh, g['obj_history'], rtol=1e-6)
+    assert np.allclose(E.W, g['W'], rtol=1e-5, atol=1e-8) and np.allclose(E.T, g['T'], rtol=1e-5, atol=1e-8)
+    assert abs(E.score(X) - float(g['score'][0])) < 1e-6
+    # reconstruction_err_ = ||M o (X - WT)||_F over the training entries, from the engine
+    Xtr_err = E.reconstruction_err_
+    assert Xtr_err > 0 and np.isfinite(Xtr_err)
+    # the returned objective calculator no longer pins the engine and can be pickled; it can still re-evaluate
+    import pickle
+    oc = pickle.loads(pickle.dumps(E.nmf_outputs['obj_calculator']))
+    assert oc.engine is None and abs(oc.true_objective() - oh[-1]) < 1e-9 * oh[-1]
+
+
 def test_convergence_TM_Estimator_and_resume(R):
     """tests/test_nmf.py:90-109: ||X-WT|| < ||X|| and fit(2) + 8 x one_iter (+ final projection) == fit(10)"""
     X = golden('text_tm_f64.npz')['X']
     n, d = X.shape
     M = R.NMF_TM_Estimator(n, d, 5, random_state=0, max_iter=10).fit(X)
     assert np.linalg.norm(X - np.dot(M.W, M.T), 'fro') < np.linalg.norm(X, 'fro')
+    assert abs(M.reconstruction_err_ - np.linalg.norm(X - np.dot(M.W, M.T), 'fro')) < 1e-9
     M2 = R.NMF_TM_Estimator(n, d, 5, random_state=0, max_iter=2, do_final_project_W=False).fit(X)
     M2.max_iter = 10
     for _ in range(8):

@@ -399,3 +399,31 @@ def test_masked_sum_constrained_T(R, order, form):
         out = run(R, sp.csr_matrix(X * M), 6, W0, T0, update_order=order, **kw)
     assert relfro(out['W'], o['W']) < F64_TOL and relfro(out['T'], o['T']) < F64_TOL
     assert np.allclose(out['T'].sum(1), 1.0, atol=1e-12)
+
+
+def test_objective_through_the_contraction(R, cuda_device):
+    """nmf.py:71-94 evaluated as ||X||^2 - 2<X T', W> + <W'W, T T'> from the block-order sweep's own contraction (no
+    pass over X per evaluation): fp64 agrees with the oracle's explicit objective to 1e-9 relative per sweep, IEEE
+    fp32 with the explicit device pass to 1e-4; with TF32 operands the difference of large terms keeps ~1e-3."""
+    X, W0, T0 = orc.synth(1500, 900, 12, 12, sigma=0.05, seed=31)
+    o = orc.nmf_oracle(X, 12, W0, T0, max_iter=6, order='hals', compute_obj_each_iter=True, eps_stop=-1.0)
+    g = run(R, X, 12, W0, T0, max_iter=6, update_order='hals', compute_obj_each_iter=True)       # 'auto' -> contraction
+    assert g['obj_calculator'].via_contraction
+    assert np.allclose(g['obj_history'], o['obj_history'], rtol=1e-9)
+    e = run(R, X, 12, W0, T0, max_iter=6, update_order='hals', compute_obj_each_iter=True, objective='exact')
+    assert not e['obj_calculator'].via_contraction and np.allclose(e['obj_history'], o['obj_history'], rtol=1e-10)
+    # engine level, fp32: explicit pass vs contraction form, with and without reuse of the sweep's contraction
+    Xf = torch.from_numpy(X.astype(np.float32)).to(cuda_device)
+    for math, tol in (('ieee', 1e-4), ('tf32', 2e-2)):
+        eng = R.RRIEngine(Xf, 12, order='hals', math=math)
+        W = torch.from_numpy(W0.astype(np.float32)).to(cuda_device)
+        T = torch.from_numpy(T0.astype(np.float32)).to(cuda_device)
+        eng.sweeps(W, T, 3, eng.params())
+        exact = eng.objective(W, T)
+        reuse = eng.objective(W, T, via_contraction=True, reuse_last_sweep=True)
+        fresh = eng.objective(W, T, via_contraction=True)
+        assert abs(reuse / exact - 1) < tol and abs(fresh / exact - 1) < tol, (math, exact, reuse, fresh)
+        assert abs(reuse / fresh - 1) < 1e-6 * (1 if math == 'ieee' else 1e3)
+        eng.close()
+    with pytest.raises(ValueError):
+        run(R, X, 12, W0, T0, max_iter=1, update_order='rri', compute_obj_each_iter=True, objective='contraction')

@@ -161,3 +161,20 @@ def test_RS_estimator_sparse_equals_dense(R):
         assert abs(Es.reconstruction_err_ - Ed.reconstruction_err_) < 1e-8 * Ed.reconstruction_err_
         assert Es.score(X) < 1.0
     assert relfro(Es.transform(sp.csr_matrix(X)), Ed.transform(X)) < 1e-8
+
+
+def test_sparse_residual_carried_across_sweeps(cuda_device):
+    """sparse_refresh_every > 1: the two residual copies continue from sweep to sweep inside one engine call (with the
+    pending rank-one record crossing the sweep boundary) instead of being rebuilt from the factors; in fp64 the
+    iterates agree with the restart-every-sweep run to rounding, and the call is still exact against the oracle."""
+    import scipy.sparse as sp
+    import rri_nmf_b200 as R
+    X, W0, T0, M = orc.synth(300, 210, 6, 7, sigma=0.05, seed=21, mask_density=0.2)
+    Xs = sp.csr_matrix(X * M)
+    o = orc.nmf_oracle(X, 7, W0, T0, max_iter=9, W_mat=M, t_row_sum=1.0)
+    kw = dict(W_in=W0, T_in=T0, max_iter=9, t_row_sum=1.0, reset_topic_method=None, max_time=1e9, sweeps_per_call=16)
+    a = R.nmf(Xs, 7, sparse_refresh_every=1, **kw)
+    b = R.nmf(Xs, 7, sparse_refresh_every=4, **kw)
+    assert relfro(a['W'], o['W']) < 1e-9 and relfro(a['T'], o['T']) < 1e-9
+    assert relfro(b['W'], o['W']) < 1e-9 and relfro(b['T'], o['T']) < 1e-9
+    assert relfro(b['W'], a['W']) < 1e-11

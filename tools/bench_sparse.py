@@ -1,5 +1,5 @@
 """Timing of the observed-entries (sparse) WRRI path at config-4 shape, next to the dense masked path on the same
-data:  python tools/bench_sparse.py [rows] [order] [sweeps] [--dense]
+data:  python tools/bench_sparse.py [rows] [order] [sweeps] [refresh_every] [--dense]
 Prints one JSON line per path; bytes/sweep is the algorithmic figure of DESIGN.md (2k passes of 10 B per entry:
 2 B block-local index + 4 B residual read + 4 B residual written)."""
 import json, os, sys, time
@@ -11,6 +11,7 @@ args = [a for a in sys.argv[1:] if not a.startswith('--')]
 rows = int(args[0]) if len(args) > 0 else 100000
 order = args[1] if len(args) > 1 else 'rri'
 sweeps = int(args[2]) if len(args) > 2 else 5
+refresh_every = int(args[3]) if len(args) > 3 else 1
 d, k, density = 20000, 50, 0.05
 dev = torch.device('cuda:0')
 g = torch.Generator(device=dev); g.manual_seed(0)
@@ -26,13 +27,13 @@ del U, V
 
 def timed(eng, label, extra):
     W, T = W0.clone(), T0.clone()
-    p = eng.params(ub_t=1.0)
+    p = eng.params(ub_t=1.0, sp_refresh_every=refresh_every)
     eng.sweeps(W, T, 1, p)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record(); eng.sweeps(W, T, sweeps, p, want_flags=False); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / sweeps
-    out = {'path': label, 'order': order, 'rows': rows, 'd': d, 'k': k, 'nnz': nnz, 'ms_per_sweep': round(ms, 3),
+    out = {'path': label, 'order': order, 'refresh_every': refresh_every, 'rows': rows, 'd': d, 'k': k, 'nnz': nnz, 'ms_per_sweep': round(ms, 3),
            'sweeps_per_s': round(1000.0 / ms, 2), 'rel_err': round(eng.rel_error(W, T), 5)}
     out.update(extra(ms))
     print(json.dumps(out), flush=True)

@@ -4,7 +4,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-import rri_nmf_b200.nmf as N
+import importlib
+import rri_nmf_b200
+N = importlib.import_module("rri_nmf_b200.nmf")
 
 gb = float(sys.argv[1]) if len(sys.argv) > 1 else 8.0
 dev = torch.device('cuda:0')
