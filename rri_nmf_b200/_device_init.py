@@ -3,9 +3,10 @@
 Behavioural reference: initialization.py:80-163 -- Boutsidis & Gallopoulos NNDSVD on a randomized partial SVD
 (`sklearn.utils.extmath.randomized_svd`: Gaussian test matrix from the NumPy generator, normalised power
 iterations, QR, SVD of the (k+10)-row projection, `svd_flip`).  The host version in `_host.py` needs X in host
-memory and, at 200k x 20k, minutes of CPU time; here X stays where the sweep engine will read it and the 2*n_iter+2
-streaming passes are library GEMMs (torch.matmul: k+10 columns, not a hot-path kernel of this repo), the small
-factorisations `torch.linalg.qr/svd`.  The same torch code runs on CPU tensors, which is how it is checked
+memory and, at 200k x 20k, minutes of CPU time; here X stays where the sweep engine will read it, the 2*n_iter+2
+streaming passes over it run through the engine's own contraction kernel (rri_gemm_nt with k+10 columns; library
+GEMMs only when no engine is at hand: CPU tensors, the masked product W_mat o X), the small factorisations are
+`torch.linalg.qr/svd`.  The same torch code runs on CPU tensors, which is how it is checked
 against `_host.initialize_nmf` without a GPU (tests/test_device_init_cpu.py).
 """
 import numpy as np
@@ -23,28 +24,48 @@ def _span_normalize(A):
     return Q
 
 
-def randomized_svd_torch(M, n_components, random_state=None, n_oversamples=10):
+class _TorchProducts(object):
+    """the two streaming products of the randomized SVD as library GEMMs (CPU tensors, or no engine at hand)"""
+
+    def __init__(self, M):
+        self.M = M
+
+    def right(self, Q):          # M @ Q      [n, r]
+        return self.M @ Q
+
+    def left(self, Q):           # M' @ Q     [d, r]
+        return self.M.t() @ Q
+
+
+def randomized_svd_torch(M, n_components, random_state=None, n_oversamples=10, products=None):
     """sklearn.utils.extmath.randomized_svd(M, n_components, random_state=...) with its defaults
     (n_iter='auto', transpose='auto', flip_sign=True; the power iterations are re-orthonormalised by a thin QR where
     sklearn's 'auto' uses LU -- same subspace) on M's device.
     M: dense 2-D torch tensor (float32 or float64); it is only ever used as a GEMM operand (no copy, no transpose
-    materialised).  Returns (U[n,k], s[k], Vt[k,d])."""
+    materialised).  `products` (optional): object with right(Q) = M @ Q and left(Q) = M' @ Q -- the sweep engine's
+    own streaming contraction (`RRIEngine.products`, rri_gemm_nt: the tcgen05 kernel in TF32 mode, the IEEE SIMT
+    kernel otherwise) -- so that the 2*n_iter + 2 passes over X run through the repo's kernels.
+    Returns (U[n,k], s[k], Vt[k,d])."""
+    P = products if products is not None else _TorchProducts(M)
     rs = _rng(random_state)
     n_random = n_components + n_oversamples
     n_samples, n_features = M.shape
     n_iter = 7 if n_components < 0.1 * min(M.shape) else 4
     transpose = n_samples < n_features
-    A = M.t() if transpose else M
-    Q = rs.normal(size=(A.shape[1], n_random))
+    # A = M' when transposed: A @ Q = M' @ Q (left product), A' @ Q = M @ Q (right product)
+    A_mm = P.left if transpose else P.right
+    At_mm = P.right if transpose else P.left
+    A_cols = n_samples if transpose else n_features
+    Q = rs.normal(size=(A_cols, n_random))
     if M.dtype == torch.float32:
         Q = Q.astype(np.float32, copy=False)
     Q = torch.from_numpy(Q).to(M.device)
     normalize = _span_normalize if n_iter > 2 else (lambda x: x)
     for _ in range(n_iter):
-        Q = normalize(A @ Q)
-        Q = normalize(A.t() @ Q)
-    Q, _ = torch.linalg.qr(A @ Q, mode='reduced')
-    B = Q.t() @ A
+        Q = normalize(A_mm(Q))
+        Q = normalize(At_mm(Q))
+    Q, _ = torch.linalg.qr(A_mm(Q), mode='reduced')
+    B = At_mm(Q).t()                         # Q'A as the transpose of A'Q
     Uhat, s, Vt = torch.linalg.svd(B, full_matrices=False)
     del B
     U = Q @ Uhat
@@ -63,7 +84,7 @@ def randomized_svd_torch(M, n_components, random_state=None, n_oversamples=10):
     return U[:, :k], s[:k], Vt[:k, :]
 
 
-def initialize_nmf_torch(X, n_components, init=None, eps=1e-6, random_state=None):
+def initialize_nmf_torch(X, n_components, init=None, eps=1e-6, random_state=None, products=None):
     """initialize_nmf (initialization.py:9-163, `_host.initialize_nmf`) for a dense torch tensor X on any device;
     returns torch tensors (W[n,k], T[k,d]) on X's device.  'random' / 'smart_random' draw from the NumPy generator
     on the host exactly like the reference (n*k + k*d numbers) and upload."""
@@ -86,7 +107,7 @@ def initialize_nmf_torch(X, n_components, init=None, eps=1e-6, random_state=None
     if init not in ('nndsvd', 'nndsvda', 'nndsvdar'):
         raise ValueError('Invalid init parameter: got %r instead of one of %r'
                          % (init, (None, 'random', 'smart_random', 'nndsvd', 'nndsvda', 'nndsvdar')))
-    U, S, Vt = randomized_svd_torch(X, k, random_state=random_state)
+    U, S, Vt = randomized_svd_torch(X, k, random_state=random_state, products=products)
     U, Vt = U.contiguous(), Vt.contiguous()
     # every singular pair is split into its positive and negative parts; per component the sign pattern carrying
     # more mass is kept (initialization.py:113-139); the leading pair is used as is up to sign (:108-109)

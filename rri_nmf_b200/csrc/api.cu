@@ -504,7 +504,8 @@ static int bind_impl(rri_handle_t h, cudaStream_t st)
         if (ws_alloc(h, &h->colsum_part, es * (size_t)ubm * k)) return 1;
         if (h->math == RRI_MATH_TF32) {
             std::string err;
-            h->tf32 = tf32_gemm_create(h->sm_count, k, err);
+            // (k + 16: the device-resident NNDSVD runs its randomized SVD with k + 10 columns through this kernel)
+            h->tf32 = tf32_gemm_create(h->sm_count, k + 16 < 256 ? k + 16 : 256, err);
             if (!h->tf32) return fail("tf32 contraction unavailable: %s", err.c_str());
         }
     }

@@ -318,8 +318,11 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 
 
 // ------------------------------------------------------------------------------------------------
-// TMA-staged variant (default).  Warp 0 = operand TMA + MMA issue, warp 1 = producer that streams the X tile and the
-// mask tile through a ring of shared-memory stages several tiles ahead, warps 2-17 = epilogue.  One CTA per SM.
+// TMA-staged variant (default).  Warp 0 = MMA issue, warp 1 = operand producer (the W / T' tile that changes with
+// the tile, ring of 2), warp 2 = producer that streams the X tile and the mask tile through a ring of shared-memory
+// stages several tiles ahead, warps 3-18 = epilogue.  One CTA per SM.  (With the operand refill issued by the MMA
+// thread itself -- after waiting for its MMAs to retire -- the epilogue spent 37 % of its samples waiting for the
+// next accumulator: profiles/r02_ncu_masked_v2.txt.)
 //
 // Epilogue without block barriers: epilogue warp (q, g) owns rows [32q, 32q+32) x columns [16g, 16g+16) of every
 // 128 x 64 tile.  It reads exactly that block of the product straight from TMEM into registers (one tcgen05.ld,
@@ -331,7 +334,8 @@ wrri_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 // two 512-thread barriers per tile: ~3400 cycles per tile where the HBM rate needs ~1750.)
 // ------------------------------------------------------------------------------------------------
 constexpr int EPI_WARPS_TMA = 16;                    // 4 warps per TMEM lane quarter (16 columns each)
-constexpr int THREADS_TMA = 32 * (2 + EPI_WARPS_TMA);
+constexpr int SERVICE_WARPS_TMA = 3;                  // MMA issue, operand TMA, X / mask TMA
+constexpr int THREADS_TMA = 32 * (SERVICE_WARPS_TMA + EPI_WARPS_TMA);
 constexpr int X_BOX_BYTES = TM * 32 * 4;             // one 32-column swizzled box of the X tile: 16 KB
 constexpr int X_TILE_BYTES = 2 * X_BOX_BYTES;        // 32 KB
 
@@ -418,23 +422,16 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================================ operand TMA + MMA control thread ========================
+        // ================================ MMA issue ================================================
         if (lane == 0 && ntiles > 0) {
-            const CUtensorMap* tm_fixed = MODE == 0 ? &tmT : &tmW;
-            const CUtensorMap* tm_var = MODE == 0 ? &tmW : &tmT;
-            mbar_expect_tx(fixed_full, (uint32_t)fixed_bytes);
-            for (int c = 0; c < nchunk; ++c) tma_load_2d(tm_fixed, sm_fixed + c * fixed_chunk, fixed_full, c * BK, fixed_tile * fixed_rows);
             const int S = p.stages;
-            for (int s0 = 0; s0 < S && s0 < ntiles; ++s0) {
-                mbar_expect_tx(&var_full[s0], (uint32_t)var_bytes);
-                for (int c = 0; c < nchunk; ++c)
-                    tma_load_2d(tm_var, sm_var + (size_t)s0 * var_bytes + c * var_chunk, &var_full[s0], c * BK, (vb + s0) * var_rows);
-            }
             mbar_wait(fixed_full, 0);
             const uint32_t idesc = make_idesc_tf32(TM, TN);
+            int s = 0;
+            uint32_t vph = 0;
             for (int n = 0; n < ntiles; ++n) {
-                const int s = n % S, a = n & 1;
-                mbar_wait(&var_full[s], (n / S) & 1);
+                const int a = n & 1;
+                mbar_wait(&var_full[s], vph);
                 mbar_wait(&acc_free[a], ((n >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t var0 = smem_u32(sm_var + (size_t)s * var_bytes), fix0 = smem_u32(sm_fixed);
@@ -447,24 +444,38 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
                                   make_desc(t0 + c * T_CHUNK_BYTES + ks * UK * 4), idesc, (c > 0 || ks > 0) ? 1u : 0u);
                     }
                 }
-                umma_commit(&var_free[s]);
+                umma_commit(&var_free[s]);            // the operand stage may be refilled when these MMAs retire
                 umma_commit(&acc_full[a]);
-                if (n + S < ntiles) {
-                    mbar_wait(&var_free[s], (n / S) & 1);
-                    mbar_expect_tx(&var_full[s], (uint32_t)var_bytes);
-                    for (int c = 0; c < nchunk; ++c)
-                        tma_load_2d(tm_var, sm_var + (size_t)s * var_bytes + c * var_chunk, &var_full[s], c * BK, (vb + n + S) * var_rows);
-                }
+                if (++s == S) { s = 0; vph ^= 1u; }
             }
         }
     } else if (warp == 1) {
+        // ================================ operand producer =========================================
+        if (lane == 0 && ntiles > 0) {
+            const CUtensorMap* tm_fixed = MODE == 0 ? &tmT : &tmW;
+            const CUtensorMap* tm_var = MODE == 0 ? &tmW : &tmT;
+            mbar_expect_tx(fixed_full, (uint32_t)fixed_bytes);
+            for (int c = 0; c < nchunk; ++c) tma_load_2d(tm_fixed, sm_fixed + c * fixed_chunk, fixed_full, c * BK, fixed_tile * fixed_rows);
+            const int S = p.stages;
+            int s = 0;
+            uint32_t vph = 0;
+            for (int n = 0; n < ntiles; ++n) {
+                mbar_wait(&var_free[s], vph ^ 1u);    // the MMAs that read this stage have retired (free at the start)
+                mbar_expect_tx(&var_full[s], (uint32_t)var_bytes);
+                for (int c = 0; c < nchunk; ++c)
+                    tma_load_2d(tm_var, sm_var + (size_t)s * var_bytes + c * var_chunk, &var_full[s], c * BK, (vb + n) * var_rows);
+                if (++s == S) { s = 0; vph ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
         // ================================ X / mask producer =======================================
         if (lane == 0) {
             const int NS = p.xm_stages;
-            for (int n = 0; n < ntiles; ++n) {
-                const int s = n % NS;
+            int s = 0;
+            uint32_t xph = 0;
+            for (int n = 0; n < ntiles; ++n, s = (s + 1 == NS ? 0 : s + 1), xph ^= (s == 0 ? 1u : 0u)) {
                 const int rt = MODE == 0 ? (vb + n) : fixed_tile, ctile = MODE == 0 ? fixed_tile : (vb + n);
-                mbar_wait(&xm_free[s], ((n / NS) & 1) ^ 1);            // every epilogue warp has released this stage
+                mbar_wait(&xm_free[s], xph ^ 1u);                      // every epilogue warp has released this stage
                 mbar_expect_tx(&xm_full[s], (uint32_t)XM_STAGE);
                 uint8_t* dst = sm_xm + (size_t)s * XM_STAGE;
                 tma_load_2d(&tmX, dst, &xm_full[s], ctile * TN, rt * TM);
@@ -479,7 +490,7 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
     } else {
         // ======================================= epilogue ========================================
-        const int ew = warp - 2;                 // 0..15
+        const int ew = warp - SERVICE_WARPS_TMA; // 0..15
         const int q = warp & 3;                  // TMEM lane quarter this warp may read
         const int cgp = ew >> 2;                 // column group: tile columns [16*cgp, 16*cgp + 16)
         const int row = q * 32 + lane;           // row of the tile this thread owns
@@ -492,7 +503,10 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         uint32_t xoff[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) xoff[j] = (uint32_t)(((((c0 & 31) >> 2) + j) ^ (row & 7)) << 4);
-        const uint32_t mrow = smem_u32(sm_xm) + (uint32_t)(X_TILE_BYTES + row * TN + c0);      // byte mask: 16 bytes
+        // byte mask: 16 bytes of a 64-byte row, stored with the 64-byte swizzle (16-byte chunk index XOR (row >> 1) & 3:
+        // eight consecutive rows then cover all 32 banks; unswizzled the read was a 4-way conflict, as many wavefronts
+        // as the four X loads together)
+        const uint32_t mrow = smem_u32(sm_xm) + (uint32_t)(X_TILE_BYTES + row * TN + (((c0 >> 4) ^ ((row >> 1) & 3)) << 4));
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
 
         // With u = X - WT (the full residual) the statistics of nmf.py:687-701 / :735-746 are
@@ -603,7 +617,7 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         // ---- once per CTA: cross-warp reduction through the (now idle) stage buffers, fixed order
         epi_barrier_tma();
         float* red = reinterpret_cast<float*>(sm_xm);
-        const int et = threadIdx.x - 64;                              // 0..511
+        const int et = threadIdx.x - 32 * SERVICE_WARPS_TMA;          // 0..511
         if (MODE == 0) {
             // red[which][col 0..63][row 0..127]: column sums over the 128 rows of the tile position
 #pragma unroll
@@ -771,7 +785,7 @@ static bool tma_prepare(WrriTc* g, const float* X, int64_t ldx, const void* M, i
     const size_t mes = mk == MK_U8 ? 1 : 4;
     if ((reinterpret_cast<uintptr_t>(X) & 15) || (ldx * 4) % 16 || (reinterpret_cast<uintptr_t>(M) & 15) || (ldm * mes) % 16) return false;
     // fp32 tiles are fetched as 32-column boxes with the 128-byte swizzle (conflict-free row-per-lane reads in the
-    // epilogue); the byte mask as one unswizzled 64-column box
+    // epilogue); the byte mask as one 64-column box with the 64-byte swizzle
     auto enc = [&](CUtensorMap* tm, const void* base, CUtensorMapDataType dt, size_t es, int64_t ld, int box_cols,
                    CUtensorMapSwizzle sw) -> bool {
         cuuint64_t gdim[2] = {(cuuint64_t)g->d, (cuuint64_t)g->n};
@@ -783,7 +797,7 @@ static bool tma_prepare(WrriTc* g, const float* X, int64_t ldx, const void* M, i
     };
     if (!enc(&g->tmX, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ldx, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
     if (mk == MK_U8) {
-        if (!enc(&g->tmM, M, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ldm, TN, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+        if (!enc(&g->tmM, M, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, ldm, TN, CU_TENSOR_MAP_SWIZZLE_64B)) return false;
     } else {
         if (!enc(&g->tmM, M, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ldm, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return false;
     }

@@ -297,10 +297,42 @@ class RRIEngine(object):
         """C = A @ B.T through the engine's contraction kernel (unit tests / roofline)."""
         M, K = A.shape
         N = B.shape[0]
+        if A.stride(1) != 1 or B.stride(1) != 1 or B.shape[1] != K:
+            raise ValueError('gemm_nt takes K-contiguous operands A[M,K], B[N,K]')
         Cm = torch.empty(M, N, dtype=A.dtype, device=A.device)
         check(self.lib.rri_gemm_nt(self.h, _ptr(A), int(A.stride(0)), _ptr(B), int(B.stride(0)), _ptr(Cm), N,
                                    M, N, K, self._stream()))
         return Cm
+
+    def products(self):
+        """The two streaming products of a randomized SVD of X through the engine's contraction kernel (used by the
+        device-resident NNDSVD initialisation): right(Q) = X @ Q, left(Q) = X' @ Q.  The transposed
+        product needs the engine's K-contiguous copy of X' (block-order handles); without it that one product is
+        a library GEMM."""
+        eng = self
+        v = 16 // self.X.element_size()
+
+        def kmajor(Q):
+            """Q' [r, K] with a 16-byte aligned row stride (a legal TMA operand)"""
+            K, r = Q.shape
+            ld = (K + v - 1) // v * v
+            B = torch.zeros((r, ld), dtype=eng.dtype, device=eng.device)
+            B[:, :K] = Q.t()
+            return B[:, :K]
+
+        aligned = self.X.stride(0) % v == 0 and self.X.data_ptr() % 16 == 0
+
+        class _P(object):
+            def right(self, Q):
+                if not aligned or Q.shape[1] > 256:
+                    return eng.X @ Q.to(eng.dtype)
+                return eng.gemm_nt(eng.X, kmajor(Q))
+
+            def left(self, Q):
+                if eng.Xt is None or Q.shape[1] > 256:
+                    return eng.X.t() @ Q.to(eng.dtype)
+                return eng.gemm_nt(eng.Xt[:, :eng.n], kmajor(Q))
+        return _P()
 
     def profile_kernel(self, which, W, T, iters=5):
         """average launch duration (ms) of the dominant streaming kernel, timed with CUDA events on the

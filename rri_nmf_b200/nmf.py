@@ -184,14 +184,16 @@ def _normalize_rows(A):
     return out
 
 
-def _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum):
+def _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum, products=None):
     """nmf.py:840-850 (initialize_nmf on W_mat o X, then the row normalisations) with X staying on its device:
-    initialization.py:80-163 through `_device_init.initialize_nmf_torch`."""
+    initialization.py:80-163 through `_device_init.initialize_nmf_torch`.  products: the engine's streaming
+    contraction for the passes over X (unmasked data only: with W_mat the matrix being factorised is W_mat o X)."""
     Xi = Xd
     if W_mat is not None:
         Mi = W_mat if isinstance(W_mat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(W_mat))
         Xi = Xd * Mi.to(device=Xd.device, dtype=Xd.dtype)
-    Wi, Ti = initialize_nmf_torch(Xi, k, init, random_state=random_state)
+        products = None
+    Wi, Ti = initialize_nmf_torch(Xi, k, init, random_state=random_state, products=products)
     del Xi
     if t_row_sum is not None:
         Ti = _normalize_rows(Ti) * t_row_sum
@@ -413,34 +415,38 @@ def nmf(X, k, w_row=None, W_mat=None, fix_W=False, fix_T=False, random_state=Non
             Xd, W_mat = _sparse_to_device(X, W_mat, device, dtype)
         else:
             Xd = _to_device(X, device, dtype)
-        if init_on_device:
-            Wi, Ti = _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum)
-            W0 = Wi if W0 is None else W0
-            T0 = Ti if T0 is None else T0
-        # np.maximum(W_in, 0) makes copies: the caller's arrays are never mutated (nmf.py:867-868)
-        W = _to_device(W0, device, dtype).clamp(min=0).contiguous()
-        T = _to_device(T0, device, dtype).clamp(min=0).contiguous()
-        if sharded:
-            import torch.distributed as dist
-            if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
-                T = T.clone()
-            dist.broadcast(T, src=0)
-        if W.data_ptr() == (W0.data_ptr() if isinstance(W0, torch.Tensor) else 0):
-            W = W.clone()
-        if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
-            T = T.clone()
         W_mat_user = a_W_mat_user
         Md = W_mat if sparse_in else _mask_to_device(W_mat, device, dtype)   # sparse: 1-D entry weights, already there
-
-        # (no synchronisation here: the pinned host -> device copy of X keeps running while the engine allocates
-        # its workspace; the first kernel is stream-ordered behind it)
-        timing['to_device_enqueue_s'] = time.perf_counter() - _t0   # host -> device copies of X, W, T (and W_mat) issued
+        # (no synchronisation here: the host -> device copy of X keeps running while the engine allocates its
+        # workspace; the first kernel is stream-ordered behind it)
+        timing['to_device_enqueue_s'] = time.perf_counter() - _t0   # host -> device copies of X (and W_mat) issued
         _t1 = time.perf_counter()
         own_engine = engine is None
         if engine is None:
             engine = RRIEngine(Xd, k, W_mat=Md, order=update_order, math=math, comm=comm)
         timing['engine_setup_s'] = time.perf_counter() - _t1       # workspace, transposed copy of X, peer mapping
         try:
+            if init_on_device:
+                # NNDSVD where X lives; its passes over X go through the engine's own contraction kernel
+                _ti = time.perf_counter()
+                Wi, Ti = _initialize_on_device(Xd, W_mat, k, init, random_state, t_row_sum, w_row_sum,
+                                               products=engine.products() if Md is None else None)
+                torch.cuda.current_stream(device).synchronize()
+                timing['init_on_device_s'] = time.perf_counter() - _ti
+                W0 = Wi if W0 is None else W0
+                T0 = Ti if T0 is None else T0
+            # np.maximum(W_in, 0) makes copies: the caller's arrays are never mutated (nmf.py:867-868)
+            W = _to_device(W0, device, dtype).clamp(min=0).contiguous()
+            T = _to_device(T0, device, dtype).clamp(min=0).contiguous()
+            if sharded:
+                import torch.distributed as dist
+                if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
+                    T = T.clone()
+                dist.broadcast(T, src=0)
+            if W.data_ptr() == (W0.data_ptr() if isinstance(W0, torch.Tensor) else 0):
+                W = W.clone()
+            if T.data_ptr() == (T0.data_ptr() if isinstance(T0, torch.Tensor) else 0):
+                T = T.clone()
             _t2 = time.perf_counter()
             out = _solve(engine, X if sparse_in else Xd, W, T, rtv, locals())
             timing['solve_s'] = time.perf_counter() - _t2           # (rest of the H2D copy,) sweeps, device -> host copy of W, T
