@@ -500,7 +500,11 @@ static int bind_impl(rri_handle_t h, cudaStream_t st)
         if (ws_alloc(h, &h->gram_part, es * (size_t)gc * k * k)) return 1;
         h->ub_blocks_w = update_rows_blocks(n, h->sm_count);
         h->ub_blocks_t = update_rows_blocks(d, h->sm_count);
-        const int ubm = h->ub_blocks_w > h->ub_blocks_t ? h->ub_blocks_w : h->ub_blocks_t;
+        int ubm = h->ub_blocks_w > h->ub_blocks_t ? h->ub_blocks_w : h->ub_blocks_t;
+        {   // the multi-GPU T update works in 32-row blocks (peer_update_blocks)
+            const int pb = peer_update_blocks(d, h->sm_count);
+            if (pb > ubm) ubm = pb;
+        }
         if (ws_alloc(h, &h->colsum_part, es * (size_t)ubm * k)) return 1;
         if (h->math == RRI_MATH_TF32) {
             std::string err;
@@ -857,10 +861,10 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
         if (psplits > 1) { launch_reduce_parts<T>((const T*)h->Cpart, psplits, d * k, d * k, myC, st); h->launches++; }
         const PeerExchange px = peer_args(h, e);
         const int blocks = peer_update_blocks(px.row_hi - px.row_lo, h->sm_count);
-        if (!launch_peer_update_rows<T>(px, d, k, solve_args(p, true), (T*)h->colsum_part, h->flags, h->sums,
-                                        h->counters + 1, blocks, st))
-            return fail("the fused peer-memory T update does not support k = %d", k);
-        h->launches++;
+        const int nl = launch_peer_update_rows<T>(px, d, k, solve_args(p, true), G, (T*)h->colsum_part, h->flags, h->sums,
+                                                  h->counters + 1, blocks, st);
+        if (!nl) return fail("the fused peer-memory T update does not support k = %d", k);
+        h->launches += nl;
         CKL();
         return 0;
     }

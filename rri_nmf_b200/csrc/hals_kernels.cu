@@ -493,128 +493,145 @@ __device__ __forceinline__ void peer_wait_all(const unsigned* flags_local, int w
     }
 }
 
-template <typename T, int KM>
-__global__ void __launch_bounds__(TPR_ROWS)
-peer_update_rows_kernel(PeerExchange px, int64_t d, int k, T reg_l1, T reg_l2, T eps, T ub, int has_ub,
-                        T* __restrict__ colsum_part, int* __restrict__ flags, double* __restrict__ sums,
-                        unsigned* __restrict__ counter)
+// --- exchange, part 1: publish this rank's partial, wait for all ranks', add the k x k Gram partials in rank order into
+// a local buffer.  A handful of blocks; every remote load of a batch is in flight before the first add (a remote
+// load takes ~2 us: a dependent chain per element would cost world x latency).
+template <typename T>
+__global__ void __launch_bounds__(256)
+peer_gram_kernel(PeerExchange px, int64_t d, int k, T* __restrict__ Gsum)
 {
-    constexpr int LD = KM + 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* Ss = reinterpret_cast<T*>(smem_raw);
-    T* ctile = Ss + KM * KM;
-    T* ftile = ctile + TPR_ROWS * LD;
-    __shared__ unsigned s_arrival;
     const int tid = threadIdx.x;
     const int world = px.world, rank = px.rank;
-    // ---- 1. publish / wait
     if (blockIdx.x == 0 && tid < world) {
         __threadfence_system();
         peer_flag_store(px.flag1[tid] + 32 * rank, px.epoch);
     }
     peer_wait_all(px.flag1[rank], world, px.epoch, px.err);
     __syncthreads();
-    // ---- 2a. Gram: sum of the ranks' partials in rank order.  A remote load takes ~2 us, so the loads of ALL ranks for a
-    // batch of elements are issued before the first add (a dependent chain per element would cost world x latency)
     const int64_t goff = d * (int64_t)k;
-    {
-        constexpr int GB = 4;                                   // elements per thread and batch
-        for (int e0 = tid; e0 < k * k; e0 += GB * TPR_ROWS) {
-            T v[16][GB];
+    constexpr int GB = 4;
+    const int e0 = (blockIdx.x * 256 + tid) * GB;
+    if (e0 >= k * k) return;
+    T v[16][GB];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+        if (r < world) {
+            const T* Gp = reinterpret_cast<const T*>(px.part[r]) + goff;
+#pragma unroll
+            for (int u = 0; u < GB; ++u) v[r][u] = (e0 + u < k * k) ? __ldcg(Gp + e0 + u) : T(0);
+        }
+#pragma unroll
+    for (int u = 0; u < GB; ++u)
+        if (e0 + u < k * k) {
+            T acc = T(0);
 #pragma unroll
             for (int r = 0; r < 16; ++r)
-                if (r < world) {
-                    const T* Gp = reinterpret_cast<const T*>(px.part[r]) + goff;
-#pragma unroll
-                    for (int u = 0; u < GB; ++u) {
-                        const int e = e0 + u * TPR_ROWS;
-                        v[r][u] = e < k * k ? __ldcg(Gp + e) : T(0);
-                    }
-                }
-#pragma unroll
-            for (int u = 0; u < GB; ++u) {
-                const int e = e0 + u * TPR_ROWS;
-                if (e < k * k) {
-                    T acc = T(0);
-#pragma unroll
-                    for (int r = 0; r < 16; ++r)
-                        if (r < world) acc += v[r][u];
-                    Ss[(e / k) * KM + (e % k)] = acc;
-                }
-            }
+                if (r < world) acc += v[r][u];
+            Gsum[e0 + u] = acc;
         }
-        if (k < KM)                                             // zero padding of the KM x KM tile
-            for (int e = tid; e < KM * KM; e += TPR_ROWS)
-                if (e / KM >= k || e % KM >= k) Ss[e] = T(0);
+}
+
+// --- exchange, part 2 (launched right behind part 1: all partials are visible): the rank's own rows of T' in blocks
+// of PEER_ROWS = 32 rows -- many small blocks, so that the NVLink reads of a block are few dependent round trips and
+// the blocks of a slice spread over the idle SMs (a slice is d/g rows: 20 blocks of 128 rows kept 128 SMs idle and
+// serialised 16-32 remote round trips per block).  All 128 threads load and store; warp 0 runs the 32 row solves.
+constexpr int PEER_ROWS = 32;
+constexpr int PEER_THREADS = 128;
+
+template <typename T, int KM>
+__global__ void __launch_bounds__(PEER_THREADS)
+peer_update_rows_kernel(PeerExchange px, int64_t d, int k, const T* __restrict__ Gsum, T reg_l1, T reg_l2, T eps, T ub,
+                        int has_ub, T* __restrict__ colsum_part, int* __restrict__ flags, double* __restrict__ sums,
+                        unsigned* __restrict__ counter)
+{
+    constexpr int LD = KM + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* Ss = reinterpret_cast<T*>(smem_raw);
+    T* ctile = Ss + KM * KM;
+    T* ftile = ctile + PEER_ROWS * LD;
+    __shared__ unsigned s_arrival;
+    const int tid = threadIdx.x;
+    const int world = px.world, rank = px.rank;
+    for (int e = tid; e < KM * KM; e += PEER_THREADS) {
+        const int a = e / KM, b = e % KM;
+        Ss[e] = (a < k && b < k) ? Gsum[a * k + b] : T(0);
     }
     T csum = T(0);
     bool unb = false;
     __syncthreads();
     const int64_t m = px.row_hi - px.row_lo;
-    const int64_t ngroups = (m + TPR_ROWS - 1) / TPR_ROWS;
+    const int64_t ngroups = (m + PEER_ROWS - 1) / PEER_ROWS;
     T* Floc = reinterpret_cast<T*>(px.Tt[rank]);
     for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        const int64_t i0 = px.row_lo + g * TPR_ROWS;
-        const int nrow = (int)((px.row_hi - i0) < TPR_ROWS ? (px.row_hi - i0) : TPR_ROWS);
-        {   // ---- 2b. staging: contraction rows summed over the ranks (in place, over NVLink), own factor rows; the
-            // loads of all ranks for a batch of elements are in flight together (see 2a)
+        const int64_t i0 = px.row_lo + g * PEER_ROWS;
+        const int nrow = (int)((px.row_hi - i0) < PEER_ROWS ? (px.row_hi - i0) : PEER_ROWS);
+        {   // staging: contraction rows summed over the ranks (in place, over NVLink), own factor rows; the loads of all
+            // ranks for a batch of elements are in flight together
             const int tot = nrow * k;
             int rr = tid / k, cc = tid - rr * k;
-            const int dr = TPR_ROWS / k, dc = TPR_ROWS - dr * k;
+            const int dr = PEER_THREADS / k, dc = PEER_THREADS - dr * k;
             const T* Frow = Floc + i0 * k;
-            constexpr int UB = 4;
-            for (int e0 = tid; e0 < tot; e0 += UB * TPR_ROWS) {
-                T cv[16][UB], fv[UB];
-#pragma unroll
-                for (int r = 0; r < 16; ++r)
-                    if (r < world) {
-                        const T* Cp = reinterpret_cast<const T*>(px.part[r]) + i0 * k;
-#pragma unroll
-                        for (int u = 0; u < UB; ++u) {
-                            const int e = e0 + u * TPR_ROWS;
-                            cv[r][u] = e < tot ? __ldcg(Cp + e) : T(0);
-                        }
-                    }
+            constexpr int UB = sizeof(T) == 8 ? 4 : 8;
+            for (int e0 = tid; e0 < tot; e0 += UB * PEER_THREADS) {
+                T acc[UB], fv[UB];
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
-                    const int e = e0 + u * TPR_ROWS;
+                    const int e = e0 + u * PEER_THREADS;
+                    acc[u] = T(0);
                     fv[u] = e < tot ? Frow[e] : T(0);
+                }
+                for (int r0 = 0; r0 < world; r0 += 8) {                // ranks in groups of 8, added in rank order
+                    T cv[8][UB];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r0 + r < world) {
+                            const T* Cp = reinterpret_cast<const T*>(px.part[r0 + r]) + i0 * k;
+#pragma unroll
+                            for (int u = 0; u < UB; ++u) {
+                                const int e = e0 + u * PEER_THREADS;
+                                cv[r][u] = e < tot ? __ldcg(Cp + e) : T(0);
+                            }
+                        }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r0 + r < world) {
+#pragma unroll
+                            for (int u = 0; u < UB; ++u) acc[u] += cv[r][u];
+                        }
                 }
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
-                    const int e = e0 + u * TPR_ROWS;
+                    const int e = e0 + u * PEER_THREADS;
                     if (e < tot) {
-                        T acc = T(0);
-#pragma unroll
-                        for (int r = 0; r < 16; ++r)
-                            if (r < world) acc += cv[r][u];
-                        ctile[rr * LD + cc] = acc;
+                        ctile[rr * LD + cc] = acc[u];
                         ftile[rr * LD + cc] = fv[u];
                     }
                     rr += dr; cc += dc;
-                    if (cc >= k) { cc -= k; ++rr; }
+                    while (cc >= k) { cc -= k; ++rr; }
                 }
             }
         }
         __syncthreads();
-        // ---- 3. the k sequential solves
+        // the k sequential solves (nmf.py:437-447 with the Gram form of :672-676), one thread per row
         if (tid < nrow) tpr_solve_row<T, KM>(Ss, ctile, ftile, tid, k, reg_l1, reg_l2, eps, ub, has_ub != 0, unb);
         __syncthreads();
-        {   // ---- 4. fan-out: the new rows into every rank's T' (row-major) and T (transposed) replicas
+        {   // fan-out: the new rows into every rank's T' (row-major) and T (transposed) replicas
             const int tot = nrow * k;
             for (int r = 0; r < world; ++r) {
                 const int pr = (rank + r) % world;                     // start with the own copy, spread the peers
                 T* Frow = reinterpret_cast<T*>(px.Tt[pr]) + i0 * k;
                 int rr = tid / k, cc = tid - rr * k;
-                const int dr = TPR_ROWS / k, dc = TPR_ROWS - dr * k;
-                for (int e = tid; e < tot; e += TPR_ROWS) {
+                const int dr = PEER_THREADS / k, dc = PEER_THREADS - dr * k;
+                for (int e = tid; e < tot; e += PEER_THREADS) {
                     Frow[e] = ftile[rr * LD + cc];
                     rr += dr; cc += dc;
-                    if (cc >= k) { cc -= k; ++rr; }
+                    while (cc >= k) { cc -= k; ++rr; }
                 }
+                // transposed copy: thread (ii, tp0) writes (tp0 + 4j, i0 + ii): 32 consecutive addresses per warp
                 T* Ft = reinterpret_cast<T*>(px.Tk[pr]);
-                if (tid < nrow)
-                    for (int tp = 0; tp < k; ++tp) Ft[(int64_t)tp * px.ldtk + i0 + tid] = ftile[tid * LD + tp];
+                const int ii = tid % PEER_ROWS, tp0 = tid / PEER_ROWS;
+                if (ii < nrow)
+                    for (int tp = tp0; tp < k; tp += PEER_THREADS / PEER_ROWS) Ft[(int64_t)tp * px.ldtk + i0 + ii] = ftile[ii * LD + tp];
             }
             if (tid < k) {
                 T cs = T(0);
@@ -627,7 +644,7 @@ peer_update_rows_kernel(PeerExchange px, int64_t d, int k, T reg_l1, T reg_l2, T
     }
     if (unb) atomicOr(flags, 4);
     if (tid < k) colsum_part[(int64_t)blockIdx.x * k + tid] = csum;
-    // ---- 5. last block: slice sums to every rank, flag2, wait for the peers, finalise sum(T[t,:])
+    // last block: slice sums to every rank, flag2, wait for the peers, finalise sum(T[t,:])
     __threadfence_system();                            // this block's stores (local and remote) before its arrival
     __syncthreads();
     if (tid == 0) s_arrival = atomicAdd(counter, 1u);
@@ -661,30 +678,33 @@ peer_update_rows_kernel(PeerExchange px, int64_t d, int k, T reg_l1, T reg_l2, T
 
 int peer_update_blocks(int64_t rows, int sm_count)
 {
-    int64_t b = (rows + TPR_ROWS - 1) / TPR_ROWS;
-    if (b > 2 * sm_count) b = 2 * sm_count;
+    int64_t b = (rows + PEER_ROWS - 1) / PEER_ROWS;
+    if (b > 4 * sm_count) b = 4 * sm_count;
     return (int)(b < 1 ? 1 : b);
 }
 
 template <typename T>
-int launch_peer_update_rows(const PeerExchange& px, int64_t d, int k, const SolveArgs& a, T* colsum_part, int* flags,
-                            double* sums, unsigned* counter, int blocks, cudaStream_t st)
+int launch_peer_update_rows(const PeerExchange& px, int64_t d, int k, const SolveArgs& a, T* Gsum, T* colsum_part,
+                            int* flags, double* sums, unsigned* counter, int blocks, cudaStream_t st)
 {
+    const bool ok = sizeof(T) == 4 ? k <= 128 : k <= 64;
+    if (!ok) return 0;                                 // rank too wide for the thread-per-row kernel: not fused
+    peer_gram_kernel<T><<<(k * k + 1023) / 1024, 256, 0, st>>>(px, d, k, Gsum);
 #define RRI_PEER(KM)                                                                                                  \
     do {                                                                                                              \
-        const size_t smem = sizeof(T) * ((size_t)KM * KM + 2 * (size_t)TPR_ROWS * (KM + 1));                          \
+        const size_t smem = sizeof(T) * ((size_t)KM * KM + 2 * (size_t)PEER_ROWS * (KM + 1));                         \
         auto kern = peer_update_rows_kernel<T, KM>;                                                                   \
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        kern<<<blocks, TPR_ROWS, smem, st>>>(px, d, k, (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub,          \
-                                            colsum_part, flags, sums, counter);                                       \
-        return 1;                                                                                                     \
+        kern<<<blocks, PEER_THREADS, smem, st>>>(px, d, k, Gsum, (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub,         \
+                                                a.has_ub, colsum_part, flags, sums, counter);                         \
+        return 2;                                                                                                     \
     } while (0)
     if (k <= 16) RRI_PEER(16);
     if (k <= 32) RRI_PEER(32);
     if (k <= 64) RRI_PEER(64);
     if constexpr (sizeof(T) == 4) { if (k <= 128) RRI_PEER(128); }
 #undef RRI_PEER
-    return 0;                                          // rank too wide for the thread-per-row kernel: not fused
+    return 0;
 }
 
 template <typename T>
@@ -914,8 +934,8 @@ void launch_transpose(const T* A, int64_t rows, int64_t cols, int64_t lda, T* B,
     template void launch_update_rows<T>(T*, int64_t, int, const T*, int, int64_t, const T* const*,        \
                                         const T*, const SolveArgs&, T*, int64_t, T*, int*, int,            \
                                         const ColsumOut&, cudaStream_t);                                   \
-    template int launch_peer_update_rows<T>(const PeerExchange&, int64_t, int, const SolveArgs&, T*, int*,  \
-                                            double*, unsigned*, int, cudaStream_t);                        \
+    template int launch_peer_update_rows<T>(const PeerExchange&, int64_t, int, const SolveArgs&, T*, T*,    \
+                                            int*, double*, unsigned*, int, cudaStream_t);                  \
     template void launch_sum_sources<T>(const T* const*, int, int64_t, T*, cudaStream_t);                  \
     template void launch_gram<T>(const T*, int64_t, int, T*, int, T*, cudaStream_t);                      \
     template void launch_reduce_parts<T>(const T*, int, int64_t, int64_t, T*, cudaStream_t);              \

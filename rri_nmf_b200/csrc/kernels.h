@@ -100,10 +100,11 @@ struct PeerExchange {
     int* err;
 };
 int peer_update_blocks(int64_t rows, int sm_count);
-// returns 1 (launched) or 0 (rank too wide for the fused kernel)
+// returns the number of kernels launched (2: Gram sum over the ranks into Gsum[k*k], then the row updates) or 0 (rank
+// too wide for the fused kernel)
 template <typename T>
-int launch_peer_update_rows(const PeerExchange& px, int64_t d, int k, const SolveArgs& a, T* colsum_part, int* flags,
-                            double* sums, unsigned* counter, int blocks, cudaStream_t st);
+int launch_peer_update_rows(const PeerExchange& px, int64_t d, int k, const SolveArgs& a, T* Gsum, T* colsum_part,
+                            int* flags, double* sums, unsigned* counter, int blocks, cudaStream_t st);
 
 // out[c] = sum_p srcs[p][c] for c < len (fixed order) -- Gram partials of all ranks read through peer memory
 template <typename T>
