@@ -25,6 +25,9 @@ CONFIGS = {
     'cfg2': dict(n=20000, d=5000, k=32, sigma=0.05, dtype='f64'),
     'cfg3': dict(n=200000, d=20000, k=64, sigma=0.05, dtype='f32'),
     'cfg5': dict(n=1000000, d=20000, k=128, sigma=0.05, dtype='f32'),
+    # config 4: masked WRRI recommender, 5 % observed; --masked dense (0/1 byte mask next to a dense X, the reference's
+    # own data layout) or --masked sparse (the observed entries as CSR, rri_bind_csr)
+    'cfg4': dict(n=100000, d=20000, k=50, sigma=0.05, dtype='f32', density=0.05),
 }
 
 
@@ -43,6 +46,8 @@ def parse():
     ap.add_argument('--no-pageable', action='store_true', help='skip the e2e run from pageable host arrays')
     ap.add_argument('--no-rri', action='store_true', help='skip the side measurement of the reference-exact order')
     ap.add_argument('--cpu-rows', type=int, default=None)
+    ap.add_argument('--masked', default='dense', choices=['dense', 'sparse'], help='config 4: data layout of the observed entries')
+    ap.add_argument('--refresh-every', type=int, default=1, help='config 4 sparse: residual restart period (sweeps)')
     return ap.parse_args()
 
 
@@ -173,18 +178,19 @@ def _load_cpu_arm():
             refshim.REF_ROOT = REF_COPY
             ref = refshim.load()
 
-            def run(X, k, W, T, sweeps):
+            def run(X, k, W, T, sweeps, M=None):
+                kw = dict(W_mat=M, t_row_sum=1.0) if M is not None else {}
                 r = ref.nmf.nmf(X, k, W_in=W, T_in=T, max_iter=sweeps, max_time=1e9, eps_stop=-1.0,
-                                compute_obj_each_iter=False, reset_topic_method=None)
+                                compute_obj_each_iter=False, reset_topic_method=None, **kw)
                 return r['W'], r['T']
             return 'reference', run, orc
         except Exception as ex:                    # a broken copy must not take the bench line down
             sys.stderr.write('reference copy under oracle/_ref unusable (%r); timing the port\n' % (ex,))
 
-    def run(X, k, W, T, sweeps):
+    def run(X, k, W, T, sweeps, M=None):
         W, T = W.copy(), T.copy()
         for _ in range(sweeps):
-            orc.sweep(X, W, T, order='rri')
+            orc.sweep(X, W, T, M=M, order='rri', t_row_sum=1.0 if M is not None else None)
         return W, T
     return 'port', run, orc
 
@@ -199,32 +205,45 @@ def cpu_reference_sweeps(cfg, rows, sweeps, warm=1):
     ncores = len(os.sched_getaffinity(0))
     kind, run, orc = _load_cpu_arm()
     dt = np.float32 if cfg['dtype'] == 'f32' else np.float64
-    X, W0, T0 = orc.synth(rows, cfg['d'], cfg['k'], cfg['k'], sigma=cfg['sigma'], seed=0, dtype=dt)
+    M = None
+    if cfg.get('density'):
+        X, W0, T0, M = orc.synth(rows, cfg['d'], cfg['k'], cfg['k'], sigma=cfg['sigma'], seed=0, dtype=dt,
+                                 mask_density=cfg['density'])
+        M = M.astype(dt)
+    else:
+        X, W0, T0 = orc.synth(rows, cfg['d'], cfg['k'], cfg['k'], sigma=cfg['sigma'], seed=0, dtype=dt)
     W, T = np.maximum(W0, 0), np.maximum(T0, 0)
     with threadpool_limits(limits=ncores, user_api='blas'):
         info = [i for i in threadpool_info() if i.get('user_api') == 'blas']
         blas = '%s %s' % (info[0].get('internal_api'), info[0].get('version')) if info else 'unknown BLAS'
         threads = int(info[0].get('num_threads')) if info else ncores
         if warm > 0:
-            W, T = run(X, cfg['k'], W, T, warm)
+            W, T = run(X, cfg['k'], W, T, warm, M) if M is not None else run(X, cfg['k'], W, T, warm)
         t0 = time.perf_counter()
-        W, T = run(X, cfg['k'], W, T, sweeps)
+        W, T = run(X, cfg['k'], W, T, sweeps, M) if M is not None else run(X, cfg['k'], W, T, sweeps)
         dtm = (time.perf_counter() - t0) / sweeps
     full = dtm * cfg['n'] / rows
     what = ('the UNMODIFIED reference nmf() (oracle/_ref copy of src/rri_nmf, py3 shim, logger at WARNING)'
             if kind == 'reference' else 'the NumPy port oracle/rri_oracle.py of the reference sweep')
     return {'value': 1.0 / full, 'unit': 'sweeps/s', 'cores': threads, 'kind': kind,
             'sample': '%s on %d of %d rows (all %d columns, k=%d, %s): %d sweeps of the interleaved reference order '
-                      '(2k GEMV passes over X, nmf.py:415-476) timed after %d warm-up, %.3f s/sweep on the sample, scaled '
+                      '(%s) timed after %d warm-up, %.3f s/sweep on the sample, scaled '
                       'linearly in n; %s with %d BLAS threads (forced with threadpoolctl); host cores available %d'
-                      % (what, rows, cfg['n'], cfg['d'], cfg['k'], cfg['dtype'], sweeps, warm, dtm, blas, threads, ncores),
+                      % (what, rows, cfg['n'], cfg['d'], cfg['k'], cfg['dtype'], sweeps,
+                         'masked WRRI with a %.0f %% 0/1 W_mat, ub_t=1: 2k dense residual products, nmf.py:687-701, :735-746' % (100 * cfg['density'])
+                         if M is not None else '2k GEMV passes over X, nmf.py:415-476',
+                         warm, dtm, blas, threads, ncores),
             'ms_per_sweep_sample': dtm * 1e3, 'sample_rows': rows, 'blas_threads': threads,
             'host_cores': ncores}
 
 
 def cpu_sample_rows(cfg, sweeps, seconds):
     """rows of the sample so that `sweeps` reference sweeps take about `seconds` of wall time (the reference moves
-    2k x rows x d elements per sweep at roughly 40 GB/s on these hosts)"""
+    2k x rows x d elements per sweep at roughly 40 GB/s on these hosts; masked: 2k dense rows x k x d products per
+    sweep plus ~8 elementwise passes over rows x d)"""
+    if cfg.get('density'):
+        per_row = 1e-2 * cfg['k'] * cfg['k'] * cfg['d'] / (50 * 50 * 20000)      # measured: 10 ms per row and sweep, 8 cores
+        return int(min(cfg['n'], max(128, seconds / (max(1, sweeps) * per_row))))
     es = 4 if cfg['dtype'] == 'f32' else 8
     per_row = 2.0 * cfg['k'] * cfg['d'] * es / 40e9
     return int(min(cfg['n'], max(256, seconds / (max(1, sweeps) * per_row))))
@@ -240,12 +259,15 @@ def main_reference(args):
     steps = max(1, args.steps)
     # bounded sample: K timed sweeps (+ warm-up) stay around a minute of CPU time
     rows = args.cpu_rows or cpu_sample_rows(cfg, steps + min(args.warmup, 1), 60.0)
+    if cfg.get('density'):
+        steps = min(steps, 5)                    # the masked reference costs ~10 ms per row and sweep
+        rows = args.cpu_rows or cpu_sample_rows(cfg, steps + 1, 60.0)
     cb = cpu_reference_sweeps(cfg, rows, sweeps=steps, warm=max(0, min(args.warmup, 1)))
     line = {
         'impl': 'reference', 'metric': 'RRI sweeps/sec', 'value': cb['value'], 'unit': 'sweeps/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 / cb['value'], 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': cfg['dtype'], 'data': 'synthetic',
-        'config': {'workload': '%s: dense %dx%d low-rank-plus-noise, k=%d, %s' % (args.config, cfg['n'], cfg['d'], cfg['k'], cfg['dtype']),
+        'config': {'workload': '%s: dense %dx%d low-rank-plus-noise, k=%d, %s%s' % (args.config, cfg['n'], cfg['d'], cfg['k'], cfg['dtype'], ', masked WRRI (5 %% observed)' if cfg.get('density') else ''),
                    'update_order': 'rri (the reference has only the interleaved order; the GPU arm reports the same '
                                    'order under "reference_order" and the ratio under "like_for_like")',
                    'sample_rows': rows},
@@ -512,6 +534,131 @@ def main_ours(args):
     return 0
 
 
+def gen_mask_shard(torch, cfg, rows, row0, device):
+    """0/1 byte mask of the observed entries (Bernoulli(density)), per global block of GEN_BLOCK rows like gen_shard"""
+    g = torch.Generator(device=device)
+    M = torch.empty(rows, cfg['d'], device=device, dtype=torch.uint8)
+    for gb in range(row0 // GEN_BLOCK, (row0 + rows + GEN_BLOCK - 1) // GEN_BLOCK):
+        g.manual_seed(700000 + gb)
+        Mb = (torch.rand(GEN_BLOCK, cfg['d'], generator=g, device=device) < cfg['density']).to(torch.uint8)
+        lo, hi = max(row0, gb * GEN_BLOCK), min(row0 + rows, (gb + 1) * GEN_BLOCK)
+        M[lo - row0:hi - row0] = Mb[lo - gb * GEN_BLOCK:hi - gb * GEN_BLOCK]
+    return M
+
+
+def main_masked(args):
+    """config 4: masked WRRI sweeps (reference order by default), dense byte mask or observed entries as CSR"""
+    import numpy as np
+    import torch
+    import rri_nmf_b200 as R
+    if int(os.environ.get('WORLD_SIZE', '1')) != 1 or args.gpus != 1:
+        raise SystemExit('config 4 is benchmarked on one GPU (the multi-GPU masked path is covered by tests/multi_gpu_check.py)')
+    device = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    sampler = ClockSampler(0)
+    sampler.start()
+    cfg = dict(CONFIGS['cfg4'])
+    if args.rows:
+        cfg['n'] = args.rows
+    order = args.order if args.order in ('rri', 'hals') else 'rri'
+    n, d, k = cfg['n'], cfg['d'], cfg['k']
+    X, W0, T0 = gen_shard(torch, cfg, n, 0, device)
+    M = gen_mask_shard(torch, cfg, n, 0, device)
+    sparse = args.masked == 'sparse'
+    if sparse:
+        Xs = (X * M).to_sparse_csr()
+        nnz = int(Xs.values().numel())
+        eng = R.RRIEngine(Xs, k, order=order)
+        math = 'ieee'
+        alg_bytes = 10.0 * nnz                          # 2 B local index + 4 B residual read + 4 B residual written
+        kname = 'sp_pass_blocked_kernel (one half-step over the observed entries)'
+    else:
+        nnz = int(M.sum())
+        math = args.math or 'tf32'
+        eng = R.RRIEngine(X, k, W_mat=M, order=order, math=math)
+        alg_bytes = float(n) * d * 5.0                  # one read of X (fp32) and of the byte mask
+        kname = 'wrri_tc_tma_kernel (masked statistics of one half-step, W T tile on tcgen05)' if math == 'tf32' else 'wrri_tstats/wstats_kernel'
+    params = eng.params(ub_t=1.0, sp_refresh_every=args.refresh_every)
+    W, T = W0.clone(), T0.clone()
+    if args.warmup > 0:
+        eng.sweeps(W, T, args.warmup, params, want_flags=False)
+    torch.cuda.synchronize()
+    l0 = eng.stats()['kernel_launches']
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    th0 = time.time()
+    ev0.record()
+    eng.sweeps(W, T, args.steps, params, want_flags=False)
+    ev1.record()
+    torch.cuda.synchronize()
+    th1 = time.time()
+    ms_per_step = ev0.elapsed_time(ev1) / args.steps
+    time.sleep(0.12)
+    clocks = sampler.window(th0, th1)
+    sampler.stop()
+    launches = eng.stats()['kernel_launches'] - l0
+    relerr = eng.rel_error(W, T)
+    peak, peak_src = load_peaks()
+    Wc, Tc = W.clone(), T.clone()
+    kt, kw = eng.profile_kernel('masked_t', Wc, Tc, 5), eng.profile_kernel('masked_w', Wc, Tc, 5)
+    kms = 0.5 * (kt + kw)
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': load_traffic('cfg4/%s/%s/rows%d' % (args.masked, order, n)), 'peak_source': peak_src,
+                'kernel_ms': kms, 'half_step_ms': {'t_step': kt, 'w_step': kw, 'includes': 'statistics pass + solve + sum'},
+                'algorithmic_bytes_per_launch': alg_bytes, 'launches_per_sweep': 2 * k,
+                'sweep_effective_gbs': 2 * k * alg_bytes / (ms_per_step * 1e-3) / 1e9,
+                'kernel_share_of_step': 2 * k * kms / ms_per_step}
+    del Wc, Tc
+    e2e = None
+    if not args.no_e2e:
+        try:
+            eng.close()
+            Wh, Th = W0.cpu().pin_memory(), T0.cpu().pin_memory()
+            if sparse:
+                Xh = Xs.cpu()
+                kw_ = {}
+                hb = (Xh.values().numel() * 8 + Xh.crow_indices().numel() * 8 + Wh.numel() * 4 + Th.numel() * 4)
+            else:
+                Xp = torch.empty(X.shape, dtype=X.dtype, pin_memory=True); Xp.copy_(X)
+                Mp = torch.empty(M.shape, dtype=torch.uint8, pin_memory=True); Mp.copy_(M)
+                Xh, kw_ = Xp.numpy(), {'W_mat': Mp, 'math': math}
+                hb = Xp.numel() * 4 + Mp.numel() + Wh.numel() * 4 + Th.numel() * 4
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = R.nmf(Xh, k, W_in=Wh.numpy(), T_in=Th.numpy(), max_iter=args.steps, reset_topic_method=None, max_time=1e9,
+                        t_row_sum=1.0, update_order=order, device=device, sparse_refresh_every=args.refresh_every, **kw_)
+            _ = float(out['W'][0, 0])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e = {'value': args.steps / dt, 'unit': 'sweeps/s', 'h2d_bytes_per_step': hb / args.steps,
+                   'd2h_bytes_per_step': (Wh.numel() + Th.numel()) * 4 / args.steps,
+                   'what': 'rri_nmf_b200.nmf(X_host, k, W_mat / sparse X, ...) from host arrays: H2D, %d sweeps, D2H of W/T; %.3f s total' % (args.steps, dt),
+                   'rank0_phases_s': out.get('timing')}
+        except Exception as ex:
+            e2e = {'value': None, 'unit': 'sweeps/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': None, 'error': repr(ex)[:200]}
+    cpu = None
+    if not args.no_cpu:
+        rows = args.cpu_rows or cpu_sample_rows(cfg, 4, 20.0)
+        cpu = cpu_reference_sweeps(cfg, rows, sweeps=3, warm=1)
+    line = {'metric': 'RRI sweeps/sec', 'value': 1e3 / ms_per_step, 'unit': 'sweeps/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f32' + ('/tf32-mma' if math == 'tf32' else ''), 'data': 'synthetic',
+            'config': {'workload': 'cfg4: masked WRRI recommender %dx%d, %.0f %% observed (nnz = %d), k=%d, f32, ub_t=1, %s' %
+                                   (n, d, 100 * cfg['density'], nnz, k, 'observed entries as CSR + CSC' if sparse else 'dense X + 0/1 byte mask'),
+                       'update_order': order, 'math': math, 'masked': args.masked, 'refresh_every': args.refresh_every,
+                       'l2_policy': 'inputs (%.1f GB per pass) larger than L2; no flush needed' % (alg_bytes / 1e9),
+                       'final_rel_error': relerr},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks}
+    if cpu:
+        line['like_for_like'] = {'update_order': order + ' (masked WRRI, nmf.py:687-701 / :735-746) on both sides',
+                                 'gpu_value': line['value'], 'cpu_value': cpu['value'], 'ratio': line['value'] / cpu['value'],
+                                 'cpu_kind': cpu['kind'], 'cpu_cores': cpu['cores']}
+    print(json.dumps(line))
+    return 0
+
+
 if __name__ == '__main__':
     a = parse()
-    sys.exit(main_reference(a) if a.impl == 'reference' else main_ours(a))
+    if a.impl == 'reference':
+        sys.exit(main_reference(a))
+    sys.exit(main_masked(a) if a.config == 'cfg4' else main_ours(a))

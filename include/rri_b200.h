@@ -168,7 +168,9 @@ int rri_gemm_nt(rri_handle_t h, const void* A_dev, int64_t lda, const void* B_de
  *   which = 1: the W half-step contraction  X T'  (n x d -> n x k)     -- reads X once
  *   which = 2: the T half-step contraction  X' W  (d x n -> d x k)     -- reads X' once (hals handles)
  *   which = 3 / 4: one whole T / W half-step of the block order (contraction, Gram, exchange, update); these
- *              advance W_dev / T_dev and, on row shards, are collective (every rank calls with the same iters) */
+ *              advance W_dev / T_dev and, on row shards, are collective (every rank calls with the same iters)
+ *   which = 5 / 6: one masked (or observed-entries) T-step / W-step of topic 0 -- the statistics pass of
+ *              nmf.py:687-701 / :735-746 plus its solve; advances W_dev / T_dev; single-GPU handles */
 int rri_profile_kernel(rri_handle_t h, int32_t which, const void* W_dev, const void* T_dev, int32_t iters,
                        float* avg_ms_host, void* stream);
 

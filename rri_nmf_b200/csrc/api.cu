@@ -235,6 +235,9 @@ extern "C" int rri_destroy(rri_handle_t h)
 {
     if (!h) return 0;
     cudaSetDevice(h->device);
+    // Workspace blocks are parked for the next handle, which zero-fills them on the legacy default stream: nothing of
+    // this handle may still be in flight on a (possibly non-blocking) caller stream when they are handed out again.
+    cudaDeviceSynchronize();
     peer_release(h);
     for (void* p : h->allocs) cached_free(p);
     if (h->tf32) tf32_gemm_destroy(h->tf32);
@@ -1545,8 +1548,29 @@ static int profile_impl(rri_handle_t h, int which, const T* W, const T* Tm, int 
                                  cudaMemcpyDeviceToDevice, st));
         }
     }
+    SpState spS;
+    if (which == 5 || which == 6) {
+        // one masked / observed-entries half-step of topic 0 (statistics pass + solve): the pass kernel dominates
+        if (h->mk == MK_NONE) return fail("which=5/6 need a masked or observed-entries handle");
+        prm.ub_t = 1.0;
+        if (h->sparse) {
+            if (sp_load_factors<T>(h, W, Tm, st)) return 1;
+            sp_refresh<T>(h, true, true, W, st);
+        } else if (h->wtc) {
+            wrri_tc_load_factors(h->wtc, (const float*)W, (const float*)Tm, st);
+            h->launches += 2;
+        }
+    }
     for (int it = -1; it < iters; ++it) {          // one untimed warm-up launch
         if (it == 0) CK(cudaEventRecord(e0, st));
+        if (which == 5 || which == 6) {
+            T* Wm = const_cast<T*>(W); T* Tw = const_cast<T*>(Tm);
+            int rc;
+            if (h->sparse) rc = which == 5 ? sp_T_step<T>(h, Wm, Tw, 0, &prm, spS, st) : sp_W_step<T>(h, Wm, Tw, 0, &prm, spS, st);
+            else rc = which == 5 ? wrri_T_step<T>(h, Wm, Tw, 0, &prm, st) : wrri_W_step<T>(h, Wm, Tw, 0, &prm, st);
+            if (rc) return 1;
+            continue;
+        }
         if (which == 0) {
             if (h->mk != MK_NONE || h->order != RRI_ORDER_RRI) return fail("which=0 needs an unmasked rri-order handle");
             launch_rri_pass<T>((const T*)h->X, h->ldx, n, d, Tm, W, k, 1 % k, (T*)h->ypart, (T*)h->ppart, true, true, h->pp, st);

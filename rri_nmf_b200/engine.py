@@ -340,7 +340,7 @@ class RRIEngine(object):
         block-order half-step (they advance W, T and are collective on row shards)"""
         self._check_factors(W, T)
         ms = C.c_float(0)
-        idx = {'rri_pass': 0, 'gemm_w': 1, 'gemm_t': 2, 't_half': 3, 'w_half': 4}[which]
+        idx = {'rri_pass': 0, 'gemm_w': 1, 'gemm_t': 2, 't_half': 3, 'w_half': 4, 'masked_t': 5, 'masked_w': 6}[which]
         check(self.lib.rri_profile_kernel(self.h, idx, _ptr(W), _ptr(T), int(iters), C.byref(ms), self._stream()))
         return float(ms.value)
 
