@@ -38,7 +38,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=sorted(CONFIGS))
-    ap.add_argument('--order', default='hals', choices=['hals', 'rri'])
+    ap.add_argument('--order', default=None, choices=['hals', 'rri'],
+                    help="update order: default 'hals' (block order), for config 4 'rri' (the reference's interleaved order)")
     ap.add_argument('--math', default=None, choices=['ieee', 'tf32'])
     ap.add_argument('--rows', type=int, default=None, help='override n (debugging; the line then says so)')
     ap.add_argument('--no-e2e', action='store_true')
@@ -48,7 +49,10 @@ def parse():
     ap.add_argument('--cpu-rows', type=int, default=None)
     ap.add_argument('--masked', default='dense', choices=['dense', 'sparse'], help='config 4: data layout of the observed entries')
     ap.add_argument('--refresh-every', type=int, default=1, help='config 4 sparse: residual restart period (sweeps)')
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.order is None:
+        a.order = 'rri' if a.config == 'cfg4' else 'hals'
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -560,7 +564,7 @@ def main_masked(args):
     cfg = dict(CONFIGS['cfg4'])
     if args.rows:
         cfg['n'] = args.rows
-    order = args.order if args.order in ('rri', 'hals') else 'rri'
+    order = args.order
     n, d, k = cfg['n'], cfg['d'], cfg['k']
     X, W0, T0 = gen_shard(torch, cfg, n, 0, device)
     M = gen_mask_shard(torch, cfg, n, 0, device)
@@ -649,8 +653,8 @@ def main_masked(args):
                        'l2_policy': 'inputs (%.1f GB per pass) larger than L2; no flush needed' % (alg_bytes / 1e9),
                        'final_rel_error': relerr},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks}
-    if cpu:
-        line['like_for_like'] = {'update_order': order + ' (masked WRRI, nmf.py:687-701 / :735-746) on both sides',
+    if cpu and order == 'rri':
+        line['like_for_like'] = {'update_order': 'rri (masked WRRI, nmf.py:687-701 / :735-746) on both sides',
                                  'gpu_value': line['value'], 'cpu_value': cpu['value'], 'ratio': line['value'] / cpu['value'],
                                  'cpu_kind': cpu['kind'], 'cpu_cores': cpu['cores']}
     print(json.dumps(line))

@@ -630,7 +630,7 @@ wrri_tc_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
             const int o = et >> 2, part = et & 3;
             float sacc = 0.f;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) sacc += red[o * TM + part * 32 + ((r + 8 * part) & 31)];
+            for (int r = 0; r < 32; ++r) sacc += red[o * TM + part * 32 + ((r + lane) & 31)];      // bank = (r + lane) & 31
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
             sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
             if (part == 0) {

@@ -427,3 +427,18 @@ def test_objective_through_the_contraction(R, cuda_device):
         eng.close()
     with pytest.raises(ValueError):
         run(R, X, 12, W0, T0, max_iter=1, update_order='rri', compute_obj_each_iter=True, objective='contraction')
+
+
+def test_pageable_host_input_is_staged_exactly(R, cuda_device):
+    """Plain (pageable) NumPy input above 64 MB goes to the device through the threaded pinned-chunk staging of
+    nmf._pageable_to_device (53 GB/s against 11 GB/s for tensor.to()): the bytes must arrive unchanged, also when the
+    size is not a multiple of the chunk and for float64."""
+    import importlib
+    N = importlib.import_module('rri_nmf_b200.nmf')
+    rs = np.random.RandomState(5)
+    for shape, dt in (((9001, 2503), np.float32), ((4099, 2053), np.float64)):
+        a = rs.rand(*shape).astype(dt)
+        assert a.nbytes >= (64 << 20)
+        t = N._to_device(a, cuda_device, torch.float32 if dt == np.float32 else torch.float64)
+        torch.cuda.synchronize()
+        assert t.shape == shape and bool((t.cpu() == torch.from_numpy(a)).all())

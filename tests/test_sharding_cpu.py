@@ -8,6 +8,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -149,3 +150,18 @@ def test_shard_bounds_helper():
     assert shard_bounds(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
     b = shard_bounds(200000, 8)
     assert b[0] == (0, 25000) and b[-1] == (175000, 200000)
+
+
+def test_row_sharded_call_requires_both_factors():
+    """an initialisation per shard would give every rank its own T replica; nmf() refuses before touching
+    the device (the check is host logic, so it runs here without a GPU)"""
+    import rri_nmf_b200 as R
+
+    class FakeComm(object):
+        world, rank = 2, 0
+
+    X = np.random.RandomState(0).rand(20, 12)
+    with pytest.raises(ValueError, match='row-sharded'):
+        R.nmf(X, 3, comm=FakeComm())
+    with pytest.raises(ValueError, match='row-sharded'):
+        R.nmf(X, 3, comm=FakeComm(), T_in=np.ones((3, 12)))
