@@ -420,13 +420,20 @@ norms_kernel(const T* __restrict__ v, int64_t len, double* __restrict__ part)
     }
 }
 
-__global__ void norms_finalize_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out)
+// out[j] = sum_b part[2b + j], j = 0, 1 (blocks <= 256): one partial per thread, fixed shared-memory tree
+__global__ void __launch_bounds__(256)
+norms_finalize_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out)
 {
-    if (threadIdx.x < 2) {
-        double s = 0.0;
-        for (int b = 0; b < blocks; ++b) s += part[2 * (int64_t)b + threadIdx.x];
-        out[threadIdx.x] = s;
+    __shared__ double red[2][256];
+    const int b = threadIdx.x;
+    red[0][b] = b < blocks ? part[2 * b] : 0.0;
+    red[1][b] = b < blocks ? part[2 * b + 1] : 0.0;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (b < o) { red[0][b] += red[0][b + o]; red[1][b] += red[1][b + o]; }
+        __syncthreads();
     }
+    if (b < 2) out[b] = red[b][0];
 }
 
 template <typename T>
@@ -436,7 +443,7 @@ void launch_norms(const T* v, int64_t len, double* part, double* out, cudaStream
     if (blocks > 256) blocks = 256;
     if (blocks < 1) blocks = 1;
     norms_kernel<T><<<blocks, 256, 0, st>>>(v, len, part);
-    norms_finalize_kernel<<<1, 32, 0, st>>>(part, blocks, out);
+    norms_finalize_kernel<<<1, 256, 0, st>>>(part, blocks, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,13 +497,20 @@ dot_parts_kernel(const T* __restrict__ C, int parts, int64_t stride, const T* __
     }
 }
 
-__global__ void sum_partials_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out)
+// out[0] = sum_b part[b]: 256 threads, strided partial sums, then a fixed shared-memory tree (deterministic)
+__global__ void __launch_bounds__(256)
+sum_partials_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out)
 {
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int b = 0; b < blocks; ++b) s += part[b];
-        out[0] = s;
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int b = threadIdx.x; b < blocks; b += 256) s += part[b];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
     }
+    if (threadIdx.x == 0) out[0] = red[0];
 }
 
 template <typename T>
@@ -507,7 +521,7 @@ void launch_sumsq_rows(const T* A, int64_t rows, int64_t cols, int64_t lda, doub
     if (blocks > 8 * sm_count) blocks = 8 * sm_count;
     if (blocks < 1) blocks = 1;
     sumsq_rows_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(A, rows, cols, lda, part);
-    sum_partials_kernel<<<1, 32, 0, st>>>(part, (int)blocks, out);
+    sum_partials_kernel<<<1, 256, 0, st>>>(part, (int)blocks, out);
 }
 
 template <typename T>
@@ -518,7 +532,7 @@ void launch_dot_parts(const T* C, int parts, int64_t stride, const T* W, int64_t
     if (blocks > 8 * sm_count) blocks = 8 * sm_count;
     if (blocks < 1) blocks = 1;
     dot_parts_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(C, parts, stride, W, len, part);
-    sum_partials_kernel<<<1, 32, 0, st>>>(part, (int)blocks, out);
+    sum_partials_kernel<<<1, 256, 0, st>>>(part, (int)blocks, out);
 }
 
 // out[0] = 0.5 * (xsq - 2 cross + sum_ab G[a,b] H[a,b]),  out[1] = xsq      (acc = {xsq, cross})
