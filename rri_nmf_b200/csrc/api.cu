@@ -182,7 +182,6 @@ struct rri_handle_s {
     // objective through the contraction: ||X||^2 is computed once per binding; c2_valid = Cpart still holds X T' of
     // the current T (and Tt its transpose): true right after a block-order sweep
     bool xsq_valid = false, c2_valid = false;
-    bool w_sums_pending = false;
     void* Gobj = nullptr;
 };
 
@@ -821,32 +820,10 @@ static bool gram_in_contraction(rri_handle_t h)
 }
 
 template <typename T>
-static int hals_W_half(rri_handle_t h, T* W, const T* Tk, int64_t ldtk, const rri_params_t* p, bool recompute, cudaStream_t st,
-                       bool allow_fuse = false)
+static int hals_W_half(rri_handle_t h, T* W, const T* Tk, int64_t ldtk, const rri_params_t* p, bool recompute, cudaStream_t st)
 {
     const int k = h->k;
     const int64_t n = h->n, d = h->d;
-    if constexpr (sizeof(T) == 4) {
-        if (allow_fuse && recompute && h->math == RRI_MATH_TF32 && tf32_gemm_can_fuse(h->tf32, k, n)) {
-            // W half-step in ONE streaming kernel: H = T T' first (IEEE Gram of the d x k copy, two small launches), then
-            // the contraction X T' whose epilogue runs the k sequential solves of every finished row (residual form)
-            // and writes W, W' -- the row-update kernel and its pass over X T', W disappear from the sweep
-            launch_gram<T>((const T*)h->Tt, d, k, (T*)h->gram_part, h->gchunks_t, (T*)h->Hm, st);
-            const SolveArgs a = solve_args(p, false);
-            Tf32Fuse f;
-            f.F = (float*)W; f.Ft = (float*)h->Wt; f.ldft = h->ldwt; f.H = (const float*)h->Hm;
-            f.reg_l1 = (float)a.reg_l1; f.reg_l2 = (float)a.reg_l2; f.eps = (float)a.eps; f.ub = (float)a.ub; f.has_ub = a.has_ub;
-            f.flags = h->flags;
-            std::string err;
-            const int nl = tf32_gemm_run(h->tf32, (const float*)h->X, h->ldx, (const float*)Tk, ldtk, (float*)h->Cpart, k, n, k, d, st,
-                                         err, nullptr, 0, 0, nullptr, 0, &f);
-            if (nl < 0) return fail("fused W half-step failed: %s", err.c_str());
-            h->launches += 2 + nl;
-            h->w_sums_pending = true;              // sum(W[:,t]) is taken once per call (sweeps_impl)
-            CKL();
-            return 0;
-        }
-    }
     if (recompute) {
         // C2 = X T' and H = T T' (from the d x k transposed copy, or as the Gram tile of the contraction)
         const bool tc_gram = gram_in_contraction(h);
@@ -1225,16 +1202,9 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
         const int64_t ldtk = px ? h->ldtk : d;
         if (px) CK(cudaMemcpy2DAsync(Tk, (size_t)ldtk * sizeof(T), Tm, (size_t)d * sizeof(T), (size_t)d * sizeof(T), (size_t)k,
                                      cudaMemcpyDeviceToDevice, st));
-        h->w_sums_pending = false;
         for (int s = 0; s < n_sweeps; ++s) {
             if (hals_T_half<T>(h, W, Tm, p, st)) return 1;
-            if (hals_W_half<T>(h, W, Tk, ldtk, p, true, st, true)) return 1;
-        }
-        if (h->w_sums_pending) {
-            // the fused W half-step leaves no per-block column sums: sum(W[:,t]) (nmf.py:793) from the rows of W'
-            launch_rowsum_flag<T>((const T*)h->Wt, k, n, h->ldwt, h->sums, k, h->world > 1 ? 0 : 2, h->flags, st);
-            h->launches++;
-            h->w_sums_pending = false;
+            if (hals_W_half<T>(h, W, Tk, ldtk, p, true, st)) return 1;
         }
         if (px) CK(cudaMemcpy2DAsync(Tm, (size_t)d * sizeof(T), Tk, (size_t)ldtk * sizeof(T), (size_t)d * sizeof(T), (size_t)k,
                                      cudaMemcpyDeviceToDevice, st));
@@ -1615,7 +1585,7 @@ static int profile_impl(rri_handle_t h, int which, const T* W, const T* Tm, int 
             // the whole T half-step (contraction + Gram + exchange + update); collective on row shards
             if (hals_T_half<T>(h, const_cast<T*>(W), const_cast<T*>(Tm), &prm, st)) return 1;
         } else if (which == 4) {
-            if (hals_W_half<T>(h, const_cast<T*>(W), Tk, ldtk, &prm, true, st, true)) return 1;
+            if (hals_W_half<T>(h, const_cast<T*>(W), Tk, ldtk, &prm, true, st)) return 1;
         } else {
             return fail("bad kernel selector %d", which);
         }

@@ -36,7 +36,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "common.cuh"
 #include "devmem.h"
 #include "gemm_tf32_sm100.h"
 #include "tc_sm100.cuh"
@@ -64,15 +63,6 @@ struct GemmParams {
     int M2;
     float* ws;                     // [grid][2][MT*BM*N] partial slots
     int* ctr;                      // [n_super] arrival counters of split tiles (all zero between launches)
-    // fused row update (FUSE kernels): the rows of the factor F[M, N] are updated in the epilogue from the finished
-    // contraction rows, with the Gram matrix H[N, N] of the other factor (block-order half-step, residual form)
-    float* F;                      // [M, N] row-major (leading dimension N), updated in place
-    float* Ft;                     // [N, ldft] transposed copy, written
-    int64_t ldft;
-    const float* H;                // [N, N]
-    float reg_l1, reg_l2, eps, ub;
-    int has_ub;
-    int* flags;
     int stages;
     int tmem_cols;
     int nbuf;                      // TMEM accumulator buffers (2 when 2*MT*NPAD <= 512 columns)
@@ -95,73 +85,11 @@ __host__ __device__ __forceinline__ int64_t part_of(int64_t units, int parts, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row update fused into the epilogue (block-order half-step, north_star group (2) inside the streaming kernel).
-// The thread holds the finished contraction row c[0..N) in registers and owns row `grow` of the factor F.  Residual
-// form of the k sequential solves of nmf.py:464-469 (Gram form of :728-734):
-//     r[t] = c[t] - sum_j f_j H[j,t]                       (phase 1: N x N FMAs, no dependent chain)
-//     for t: x = [r[t] + f_t H[t,t] - l1]_+ / (H[t,t] + l2 + eps);  r[:] -= (x - f_t) H[t,:];  f_t = x
-// Only r lives in registers (static indices; r[t] is fetched by a select over the 8-step groups), the old f_t is
-// re-read from global memory, H rows are shared-memory broadcasts.  The epilogue warps idle ~95 % of a tile's streaming
-// time, so this hides a kernel that cost 5 % (k = 64, one GPU) of a sweep.
-// ------------------------------------------------------------------------------------------------
-template <int NPAD>
-__device__ __forceinline__ void fused_row_update(float (&r)[NPAD], bool valid, int64_t grow, const GemmParams& p,
-                                                 const float* __restrict__ Hs)
-{
-    const int N = p.N;
-    float* __restrict__ frow = p.F + grow * N;
-    // phase 1
-#pragma unroll 2
-    for (int j = 0; j < N; ++j) {
-        const float fj = valid ? frow[j] : 0.f;
-        const float4* hrow = reinterpret_cast<const float4*>(Hs + j * NPAD);
-#pragma unroll
-        for (int t4 = 0; t4 < NPAD / 4; ++t4) {
-            const float4 hv = hrow[t4];
-            r[4 * t4] = fmaf(-fj, hv.x, r[4 * t4]); r[4 * t4 + 1] = fmaf(-fj, hv.y, r[4 * t4 + 1]);
-            r[4 * t4 + 2] = fmaf(-fj, hv.z, r[4 * t4 + 2]); r[4 * t4 + 3] = fmaf(-fj, hv.w, r[4 * t4 + 3]);
-        }
-    }
-    // phase 2
-    bool unb = false;
-#pragma unroll 1
-    for (int c = 0; c < NPAD / 8; ++c) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int t = 8 * c + u;
-            if (t < N) {
-                float rt = r[u];
-#pragma unroll
-                for (int cc = 1; cc < NPAD / 8; ++cc) rt = (cc == c) ? r[8 * cc + u] : rt;
-                const float htt = Hs[t * NPAD + t];
-                const float ft = valid ? frow[t] : 0.f;
-                const float x = solve_scalar_c<float>(fmaf(ft, htt, rt) - p.reg_l1, htt + p.reg_l2, p.eps, p.ub, p.has_ub != 0, unb);
-                const float delta = x - ft;
-                const float4* hrow = reinterpret_cast<const float4*>(Hs + t * NPAD);
-#pragma unroll
-                for (int t4 = 0; t4 < NPAD / 4; ++t4) {
-                    const float4 hv = hrow[t4];
-                    r[4 * t4] = fmaf(-delta, hv.x, r[4 * t4]); r[4 * t4 + 1] = fmaf(-delta, hv.y, r[4 * t4 + 1]);
-                    r[4 * t4 + 2] = fmaf(-delta, hv.z, r[4 * t4 + 2]); r[4 * t4 + 3] = fmaf(-delta, hv.w, r[4 * t4 + 3]);
-                }
-                if (valid) {
-                    frow[t] = x;
-                    p.Ft[(int64_t)t * p.ldft + grow] = x;
-                }
-            }
-        }
-    }
-    if (unb && valid) atomicOr(p.flags, 4);
-}
-
-// ------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------
 // EWQ = epilogue warps per TMEM lane quarter (each takes NPAD/EWQ accumulator columns of every tile): 2 for
 // k <= 64, 4 for wider ranks so that a thread never holds more than 64 accumulators
-// FUSE: the epilogue warp (q, h) owns ALL columns of tile mt = h (needs EWQ == MT), and a finished tile's rows go
-// through fused_row_update before they are written (the contraction rows themselves are still stored to C).
-template <int MT, int NPAD, int EWQ, bool FUSE>
+template <int MT, int NPAD, int EWQ>
 __global__ void __launch_bounds__(64 + 128 * EWQ, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, GemmParams p, int* err)
@@ -180,7 +108,6 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     int* fix_info = reinterpret_cast<int*>(tmem_slot + 1);   // [3] arrival order / first / last contributor of a split tile
     const float** fix_src = reinterpret_cast<const float**>(full + 64);    // [<= gridDim.x] slot of every contributor
-    float* Hs = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 4096);   // FUSE: [NPAD][NPAD] Gram matrix, zero padded
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t u_begin = part_start(p.units, gridDim.x, blockIdx.x);
@@ -202,13 +129,6 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (FUSE && warp >= 2) {
-        for (int e = (int)threadIdx.x - 64; e < NPAD * NPAD; e += 128 * EWQ) {
-            const int a = e / NPAD, b = e % NPAD;
-            Hs[e] = (a < p.N && b < p.N) ? p.H[a * p.N + b] : 0.f;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(128 * EWQ) : "memory");
-    }
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
@@ -275,11 +195,9 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // 4*EWQ warps: warp (q, h) owns TMEM lanes [32q, 32q+32) and columns [h*NPAD/EWQ, (h+1)*NPAD/EWQ) of every tile
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;
-        constexpr int HC = FUSE ? NPAD : NPAD / EWQ;              // columns per thread and tile
-        constexpr int NTL = FUSE ? 1 : MT;                        // tiles per thread (FUSE: tile h, all columns)
+        constexpr int HC = NPAD / EWQ;                            // columns per thread and tile
         constexpr int EPI_THREADS = 128 * EWQ;
-        constexpr int NACC = NTL * HC;
-        const int colbase = FUSE ? 0 : h * HC;
+        constexpr int NACC = MT * HC;
         float acc[NACC];
         uint32_t run = 0;
         const int64_t slot_elems = (int64_t)MT * BM * p.N;
@@ -294,16 +212,15 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t use = p.nbuf == 2 ? (run >> 1) : run;
                 mbar_wait(&tfull[b], use & 1u, err, 4);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)(MT * NPAD) + (uint32_t)colbase;
+                const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + b * (uint32_t)(MT * NPAD) + (uint32_t)(h * HC);
 #pragma unroll
-                for (int i = 0; i < NTL; ++i) {
-                    const int mt = FUSE ? h : i;
+                for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
                     for (int c0 = 0; c0 < HC; c0 += 16) {
                         float v[16];
                         tmem_ld16(tacc + (uint32_t)(mt * NPAD + c0), v);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[i * HC + c0 + j] += v[j];     // round-to-nearest fp32 adds
+                        for (int j = 0; j < 16; ++j) acc[mt * HC + c0 + j] += v[j];     // round-to-nearest fp32 adds
                     }
                 }
                 tc_fence_before();
@@ -318,22 +235,21 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int64_t out_row0 = (aux ? s - p.n_super_main : s) * MT * BM;
             const int64_t out_rows = aux ? (int64_t)p.M2 : p.M;
             int c_lo = 0, c_hi = 0;
-            bool fused_last = false;             // FUSE: this CTA arrived last at a split tile and holds the summed rows
             if (!complete) {
                 const int slot = (u == u_begin) ? 0 : 1;
                 float* dst = p.ws + ((int64_t)blockIdx.x * 2 + slot) * slot_elems;
 #pragma unroll
-                for (int i = 0; i < NTL; ++i) {
-                    const int row = (FUSE ? h : i) * BM + q * 32 + lane;
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int row = mt * BM + q * 32 + lane;
 #pragma unroll
                     for (int c0 = 0; c0 < HC; c0 += 4) {
-                        const int col = colbase + c0;
+                        const int col = h * HC + c0;
                         float* o = dst + (int64_t)row * p.N + col;
                         if ((col + 4 <= p.N) && ((p.N & 3) == 0)) {
-                            __stcg(reinterpret_cast<float4*>(o), make_float4(acc[i * HC + c0], acc[i * HC + c0 + 1], acc[i * HC + c0 + 2], acc[i * HC + c0 + 3]));
+                            __stcg(reinterpret_cast<float4*>(o), make_float4(acc[mt * HC + c0], acc[mt * HC + c0 + 1], acc[mt * HC + c0 + 2], acc[mt * HC + c0 + 3]));
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) if (col + j < p.N) __stcg(o + j, acc[i * HC + c0 + j]);
+                            for (int j = 0; j < 4; ++j) if (col + j < p.N) __stcg(o + j, acc[mt * HC + c0 + j]);
                         }
                     }
                 }
@@ -362,27 +278,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int64_t rows_left = out_rows - out_row0;
                     const int nvalid = (int)(rows_left < (int64_t)MT * BM ? rows_left : (int64_t)MT * BM) * p.N;
                     float* tile = out + out_row0 * out_ld;
-                    if (FUSE) {
-                        // the row update below needs the summed row in this thread's registers: every thread adds its
-                        // own row over the contributors (in CTA order)
-                        const int row = h * BM + q * 32 + lane;
-#pragma unroll
-                        for (int c = 0; c < NACC; ++c) acc[c] = 0.f;
-                        for (int i = 0; i < ncontrib; ++i) {
-                            const float* src = fix_src[i] + (int64_t)row * p.N;
-#pragma unroll
-                            for (int c0 = 0; c0 < HC; c0 += 4) {
-                                if ((c0 + 4 <= p.N) && ((p.N & 3) == 0)) {
-                                    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + c0));
-                                    acc[c0] += v.x; acc[c0 + 1] += v.y; acc[c0 + 2] += v.z; acc[c0 + 3] += v.w;
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) if (c0 + j < p.N) acc[c0 + j] += __ldcg(src + c0 + j);
-                                }
-                            }
-                        }
-                        fused_last = true;
-                    } else if (out_ld == p.N && (p.N & 3) == 0) {
+                    if (out_ld == p.N && (p.N & 3) == 0) {
                         for (int e = et * 4; e < nvalid; e += EPI_THREADS * 4) {
                             float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
                             for (int i = 0; i < ncontrib; ++i) {
@@ -403,27 +299,23 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // fix_info / fix_src are reused by the next segment
             }
-            if (complete || fused_last) {
+            if (complete) {
 #pragma unroll
-                for (int i = 0; i < NTL; ++i) {
-                    const int64_t row = out_row0 + (FUSE ? h : i) * BM + q * 32 + lane;
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int64_t row = out_row0 + mt * BM + q * 32 + lane;
                     if (row < out_rows) {
 #pragma unroll
                         for (int c0 = 0; c0 < HC; c0 += 4) {
-                            const int col = colbase + c0;
+                            const int col = h * HC + c0;
                             float* o = out + row * out_ld + col;
                             if ((col + 4 <= p.N) && ((out_ld & 3) == 0)) {
-                                *reinterpret_cast<float4*>(o) = make_float4(acc[i * HC + c0], acc[i * HC + c0 + 1], acc[i * HC + c0 + 2], acc[i * HC + c0 + 3]);
+                                *reinterpret_cast<float4*>(o) = make_float4(acc[mt * HC + c0], acc[mt * HC + c0 + 1], acc[mt * HC + c0 + 2], acc[mt * HC + c0 + 3]);
                             } else {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) if (col + j < p.N) o[j] = acc[i * HC + c0 + j];
+                                for (int j = 0; j < 4; ++j) if (col + j < p.N) o[j] = acc[mt * HC + c0 + j];
                             }
                         }
                     }
-                }
-                if constexpr (FUSE) {
-                    const int64_t row = out_row0 + h * BM + q * 32 + lane;
-                    fused_row_update<NPAD>(acc, row < out_rows, row, p, Hs);
                 }
             }
             u += len;
@@ -522,13 +414,12 @@ static bool encode_2d(Tf32Gemm* g, CUtensorMap* tm, const float* base, int64_t r
     return true;
 }
 
-template <int MT, int NPAD, bool FUSE = false>
+template <int MT, int NPAD>
 static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, GemmParams p,
                    cudaStream_t st, std::string& err)
 {
     const int a_stage = MT * A_TILE_BYTES, b_stage = NPAD * BK * 4;
-    // mbarriers, TMEM slot, fix-up scratch (one slot pointer per CTA of the grid) [, the Gram matrix of a fused update]
-    const int bar_bytes = 4096 + (FUSE ? NPAD * NPAD * 4 : 0);
+    const int bar_bytes = 4096;       // mbarriers, TMEM slot, fix-up scratch (one slot pointer per CTA of the grid)
     int stages = (SMEM_LIMIT - 1024 /*alignment slack*/ - bar_bytes) / (a_stage + b_stage);
     if (stages > 8) stages = 8;
     if (stages < 2) { err = "not enough shared memory for two pipeline stages"; return -1; }
@@ -541,8 +432,7 @@ static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     p.flush = g->flush > 0 ? g->flush : (1 << 30);
     int64_t grid = p.units < g->sm_count ? p.units : g->sm_count;
     constexpr int EWQ = NPAD >= 128 ? 4 : 2;
-    static_assert(!FUSE || EWQ == MT, "the fused update needs one epilogue warp group per tile");
-    auto kern = tf32_gemm_kernel<MT, NPAD, EWQ, FUSE>;
+    auto kern = tf32_gemm_kernel<MT, NPAD, EWQ>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         err = "cudaFuncSetAttribute(max dynamic smem) failed";
         return -1;
@@ -553,15 +443,9 @@ static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     return 1;
 }
 
-bool tf32_gemm_can_fuse(const Tf32Gemm* g, int N, int64_t M)
-{
-    static const bool on = [] { const char* e = getenv("RRI_FUSE_UPDATE"); return e && *e == '1'; }();     // opt-in until measured
-    return g && on && N <= 64 && M > BM && g->force_mt != 1;
-}
-
 int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                   int64_t M, int N, int64_t K, cudaStream_t st, std::string& err, const float* A2, int64_t lda2, int M2,
-                  float* C2, int64_t ldc2, const Tf32Fuse* fuse)
+                  float* C2, int64_t ldc2)
 {
     if (!g) { err = "null contraction handle"; return -1; }
     if (N < 1 || N > 256) { err = "N must be in [1,256]"; return -1; }
@@ -594,14 +478,6 @@ int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int6
         g->ctr_len = len;
     }
     p.ctr = g->ctr;
-    p.F = nullptr; p.Ft = nullptr; p.ldft = 0; p.H = nullptr; p.reg_l1 = p.reg_l2 = p.eps = p.ub = 0.f; p.has_ub = 0; p.flags = nullptr;
-    if (fuse) {
-        if (!tf32_gemm_can_fuse(g, N, M) || mt != 2 || ldc != N) { err = "fused row update: unsupported shape"; return -1; }
-        p.F = fuse->F; p.Ft = fuse->Ft; p.ldft = fuse->ldft; p.H = fuse->H; p.reg_l1 = fuse->reg_l1; p.reg_l2 = fuse->reg_l2;
-        p.eps = fuse->eps; p.ub = fuse->ub; p.has_ub = fuse->has_ub; p.flags = fuse->flags;
-        if (npad == 32) return run_cfg<2, 32, true>(g, tmA, tmB, tmA2, p, st, err);
-        return run_cfg<2, 64, true>(g, tmA, tmB, tmA2, p, st, err);
-    }
     p.stages = 0; p.tmem_cols = 0;
     p.nbuf = 1; p.flush = 0;
 #define RRI_GEMM_CASE(MTv, NP) if (mt == MTv && npad == NP) return run_cfg<MTv, NP>(g, tmA, tmB, tmA2, p, st, err)

@@ -12,21 +12,7 @@ void tf32_gemm_destroy(Tf32Gemm* g);
 // returns the number of kernels launched, or -1 (err set).
 // Optional auxiliary output in the same launch: C2[M2, N] (leading dimension ldc2) = A2[M2, K] * B[N, K]^T -- with
 // A2 = B this is the k x k Gram matrix of the factor, computed as one more row tile of the streaming contraction.
-// Optional fused row update (N <= 64, M > 128; tf32_gemm_can_fuse): the block-order half-step of the factor F[M, N]
-// whose contraction this is runs in the kernel's epilogue -- F updated in place, its transpose written to Ft -- with
-// the Gram matrix H[N, N] of the other factor (k sequential solves per row, residual form).
-struct Tf32Fuse {
-    float* F;
-    float* Ft;
-    int64_t ldft;
-    const float* H;
-    float reg_l1, reg_l2, eps, ub;
-    int has_ub;
-    int* flags;                      // RRI_FLAG_UNBOUNDED is or-ed in when a denominator is <= 0 without a bound
-};
-bool tf32_gemm_can_fuse(const Tf32Gemm* g, int N, int64_t M);
 int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
                   int64_t ldc, int64_t M, int N, int64_t K, cudaStream_t st, std::string& err,
-                  const float* A2 = nullptr, int64_t lda2 = 0, int M2 = 0, float* C2 = nullptr, int64_t ldc2 = 0,
-                  const Tf32Fuse* fuse = nullptr);
+                  const float* A2 = nullptr, int64_t lda2 = 0, int M2 = 0, float* C2 = nullptr, int64_t ldc2 = 0);
 }  // namespace rri
