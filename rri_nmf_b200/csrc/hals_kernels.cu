@@ -450,67 +450,81 @@ static void launch_update_rows_tpr(T* F, int64_t m, int k, const T* Cpart, int p
 }
 
 // ------------------------------------------------------------------------------------------------
-// row update for wide ranks (64 < k <= 128, fp32), register-resident: the staged variant above needs a 64 KB Gram
-// matrix plus two 66 KB tiles at KM = 128 -- one 128-thread block per SM, 0.75 ms for the 125 000 rows of a config-5
-// shard.  Here only the Gram matrix sits in shared memory (three blocks per SM): a thread loads its own factor row into
-// registers with 16-byte loads, reads the contraction entry of each step straight from global memory (sequential per
-// thread: L1 lines are reused), and writes the row and its transpose itself.  Column sums are taken afterwards from
-// the transposed copy (rowsum_flag_kernel).  Same direct form as update_rows_tpr_kernel.
+// row update, register-resident (the default when the contraction comes as one slice and k is a multiple of the
+// 16-byte vector): only the Gram matrix sits in shared memory, so 3 (k = 128) to 8 blocks share an SM where the staged
+// variant above fits one or two (its two staged tiles cost 66 KB at KM = 64, 132 KB at KM = 128).  A thread loads its
+// own factor row into registers with 16-byte loads, reads the contraction entry of each step straight from global
+// memory (sequential per thread: L1 lines are reused), and writes the row and its transpose itself.  Same direct form
+// and the same order of operations as update_rows_tpr_kernel -- the results are bit-identical.  Column sums are
+// taken afterwards from the transposed copy (rowsum_flag_kernel).  Config-5 shard (125 000 rows, k = 128): W update
+// 0.73 -> 0.43 ms, T update 0.23 -> 0.13 ms (profiles/r02_update_rows_reg_ab.txt).
 // ------------------------------------------------------------------------------------------------
-template <int KM>
+template <typename T, int KM>
 __global__ void __launch_bounds__(128)
-update_rows_reg_kernel(float* __restrict__ F, int64_t m, int k, const float* __restrict__ C, const float* __restrict__ S,
-                       float reg_l1, float reg_l2, float eps, float ub, int has_ub, float* __restrict__ Ft, int64_t ldft,
+update_rows_reg_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict__ C, const T* __restrict__ S,
+                       T reg_l1, T reg_l2, T eps, T ub, int has_ub, T* __restrict__ Ft, int64_t ldft,
                        int* __restrict__ flags)
 {
+    using V = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* Ss = reinterpret_cast<float*>(smem_raw);          // [KM][KM], zero padded
+    T* Ss = reinterpret_cast<T*>(smem_raw);                  // [KM][KM], zero padded
     const int tid = threadIdx.x;
     for (int e = tid; e < KM * KM; e += 128) {
         const int a = e / KM, b = e % KM;
-        Ss[e] = (a < k && b < k) ? S[a * k + b] : 0.f;
+        Ss[e] = (a < k && b < k) ? S[a * k + b] : T(0);
     }
     __syncthreads();
     bool unb = false;
     for (int64_t row = (int64_t)blockIdx.x * 128 + tid; row < m; row += (int64_t)gridDim.x * 128) {
-        float f[KM];
-        const float4* frow4 = reinterpret_cast<const float4*>(F + row * k);       // k % 4 == 0 (checked by the launcher)
+        T f[KM];
+        const V* frowv = reinterpret_cast<const V*>(F + row * k);                  // k % VN == 0 (checked by the launcher)
 #pragma unroll
-        for (int j4 = 0; j4 < KM / 4; ++j4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (4 * j4 < k) v = frow4[j4];
-            f[4 * j4] = v.x; f[4 * j4 + 1] = v.y; f[4 * j4 + 2] = v.z; f[4 * j4 + 3] = v.w;
+        for (int jv = 0; jv < KM / VN; ++jv) {
+            T fv[VN];
+#pragma unroll
+            for (int v = 0; v < VN; ++v) fv[v] = T(0);
+            if (VN * jv < k) unpack(frowv[jv], fv);
+#pragma unroll
+            for (int v = 0; v < VN; ++v) f[VN * jv + v] = fv[v];
         }
-        const float* crow = C + row * k;
+        const T* crow = C + row * k;
 #pragma unroll 1
         for (int c = 0; c < (k + 7) / 8; ++c) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int t = 8 * c + u;
                 if (t < k) {
-                    const float4* srow = reinterpret_cast<const float4*>(Ss + t * KM);
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    const V* srow = reinterpret_cast<const V*>(Ss + t * KM);
+                    T acc[4] = {T(0), T(0), T(0), T(0)};
 #pragma unroll
-                    for (int jv = 0; jv < KM / 4; ++jv) {
-                        const float4 sv = srow[jv];
-                        acc[0] = fmaf(f[4 * jv], sv.x, acc[0]); acc[1] = fmaf(f[4 * jv + 1], sv.y, acc[1]);
-                        acc[2] = fmaf(f[4 * jv + 2], sv.z, acc[2]); acc[3] = fmaf(f[4 * jv + 3], sv.w, acc[3]);
+                    for (int jv = 0; jv < KM / VN; ++jv) {
+                        T sv[VN];
+                        unpack(srow[jv], sv);
+#pragma unroll
+                        for (int v = 0; v < VN; ++v) acc[(jv * VN + v) & 3] = fma(f[jv * VN + v], sv[v], acc[(jv * VN + v) & 3]);
                     }
-                    float ft = f[u];
+                    T ft = f[u];
 #pragma unroll
                     for (int jj = 1; jj < KM / 8; ++jj) ft = (jj == c) ? f[8 * jj + u] : ft;
-                    const float stt = Ss[t * KM + t];
-                    const float dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
-                    const float x = solve_scalar_c<float>(crow[t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
+                    const T stt = Ss[t * KM + t];
+                    const T dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
+                    const T x = solve_scalar_c<T>(crow[t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
 #pragma unroll
                     for (int jj = 0; jj < KM / 8; ++jj) f[8 * jj + u] = (jj == c) ? x : f[8 * jj + u];
                 }
             }
         }
-        float4* fout = reinterpret_cast<float4*>(F + row * k);
+        V* fout = reinterpret_cast<V*>(F + row * k);
 #pragma unroll
-        for (int j4 = 0; j4 < KM / 4; ++j4)
-            if (4 * j4 < k) fout[j4] = make_float4(f[4 * j4], f[4 * j4 + 1], f[4 * j4 + 2], f[4 * j4 + 3]);
+        for (int jv = 0; jv < KM / VN; ++jv)
+            if (VN * jv < k) {
+                V o;
+                T* op = reinterpret_cast<T*>(&o);
+#pragma unroll
+                for (int v = 0; v < VN; ++v) op[v] = f[VN * jv + v];
+                fout[jv] = o;
+            }
         if (Ft) {
 #pragma unroll
             for (int t = 0; t < KM; ++t)
@@ -518,6 +532,18 @@ update_rows_reg_kernel(float* __restrict__ F, int64_t m, int k, const float* __r
         }
     }
     if (unb) atomicOr(flags, 4);
+}
+
+template <typename T, int KM>
+static void launch_update_rows_reg(T* F, int64_t m, int k, const T* C, const T* S, const SolveArgs& a, T* Ft, int64_t ldft,
+                                   int* flags, const ColsumOut& co, cudaStream_t st)
+{
+    const size_t smem = sizeof(T) * KM * KM;
+    auto kern = update_rows_reg_kernel<T, KM>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t nb = (m + 127) / 128;
+    kern<<<(unsigned)nb, 128, smem, st>>>(F, m, k, C, S, (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft, flags);
+    if (co.sums) launch_rowsum_flag<T>(Ft, k, m, ldft, co.sums, co.off, co.zero_flag, flags, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -785,25 +811,21 @@ void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64
 {
     // thread-per-row variants while the row fits in registers / the tiles in shared memory
     // (fp32: k <= 128, fp64: k <= 64); wider ranks use the warp-per-row kernel
+    {
+        static const bool reg_off = [] { const char* e = getenv("RRI_UPDATE_REG"); return e && *e == '0'; }();
+        constexpr int VN = Vec<T>::N;
+        if (!reg_off && parts == 1 && !srcs && Ft && (k % VN) == 0 && k <= (sizeof(T) == 4 ? 128 : 64)) {
+            if (k <= 16) launch_update_rows_reg<T, 16>(F, m, k, Cpart, S, a, Ft, ldft, flags, co, st);
+            else if (k <= 32) launch_update_rows_reg<T, 32>(F, m, k, Cpart, S, a, Ft, ldft, flags, co, st);
+            else if (k <= 64) launch_update_rows_reg<T, 64>(F, m, k, Cpart, S, a, Ft, ldft, flags, co, st);
+            else if constexpr (sizeof(T) == 4) launch_update_rows_reg<T, 128>(F, m, k, Cpart, S, a, Ft, ldft, flags, co, st);
+            return;
+        }
+    }
 #define RRI_TPR(KM) launch_update_rows_tpr<T, KM>(F, m, k, Cpart, parts, part_stride, srcs, S, a, Ft, ldft, colsum_part, flags, blocks, co, st)
     if (k <= 16) { RRI_TPR(16); return; }
     if (k <= 32) { RRI_TPR(32); return; }
     if (k <= 64) { RRI_TPR(64); return; }
-    if constexpr (sizeof(T) == 4) {
-        static const bool reg_off = [] { const char* e = getenv("RRI_UPDATE_REG"); return e && *e == '0'; }();
-        if (k > 64 && k <= 128 && (k & 3) == 0 && parts == 1 && !srcs && Ft && !reg_off) {
-            // register-resident variant: three blocks per SM instead of one; column sums from the transposed copy
-            constexpr int KM = 128;
-            const size_t smem = sizeof(float) * KM * KM;
-            auto kern = update_rows_reg_kernel<KM>;
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            int64_t nb = (m + 127) / 128;
-            kern<<<(unsigned)nb, 128, smem, st>>>((float*)F, m, k, (const float*)Cpart, (const float*)S, (float)a.reg_l1,
-                                                 (float)a.reg_l2, (float)a.eps, (float)a.ub, a.has_ub, (float*)Ft, ldft, flags);
-            if (co.sums) launch_rowsum_flag_f32((const float*)Ft, k, m, ldft, co.sums, co.off, co.zero_flag, flags, st);
-            return;
-        }
-    }
     if (k <= 128 && sizeof(T) == 4) { RRI_TPR(128); return; }
 #undef RRI_TPR
     const int kl = (k + 31) / 32;

@@ -78,9 +78,6 @@ struct ColsumOut {
     int off, zero_flag;
     unsigned* counter;
 };
-// (fp32 wrapper of launch_rowsum_flag for hals_kernels.cu: the register-resident update takes its column sums from Ft)
-void launch_rowsum_flag_f32(const float* A, int rows, int64_t len, int64_t ld, double* sums, int slot0, int zero_flag,
-                            int* flags, cudaStream_t st);
 // srcs (optional, device array of `parts` pointers): slice p is srcs[p] instead of Cpart + p*part_stride.
 template <typename T>
 void launch_update_rows(T* F, int64_t m, int k, const T* Cpart, int parts, int64_t part_stride,

@@ -309,12 +309,6 @@ void launch_rowsum_flag(const T* A, int rows, int64_t len, int64_t ld, double* s
     if (rows > 0) rowsum_flag_kernel<T><<<rows, 1024, 0, st>>>(A, len, ld, sums, slot0, zero_flag, flags);
 }
 
-void launch_rowsum_flag_f32(const float* A, int rows, int64_t len, int64_t ld, double* sums, int slot0, int zero_flag,
-                            int* flags, cudaStream_t st)
-{
-    launch_rowsum_flag<float>(A, rows, len, ld, sums, slot0, zero_flag, flags, st);
-}
-
 template <typename T>
 __global__ void vec_scale_to_sum_kernel(T* __restrict__ v, int64_t len, int64_t stride,
                                         const double* __restrict__ sums, int slot, double s)
