@@ -67,6 +67,7 @@ struct GemmParams {
     int tmem_cols;
     int nbuf;                      // TMEM accumulator buffers (2 when 2*MT*NPAD <= 512 columns)
     int flush;                     // K-chunks per TMEM accumulation run
+    int reverse_tail;              // tails of split tiles stream K downward (see the producer)
 };
 
 using namespace tc;
@@ -138,7 +139,15 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int64_t u = u_begin; u < u_end;) {
                 const int64_t s = u / p.nk, kc0 = u % p.nk;
                 const int64_t len = (u_end - u) < (p.nk - kc0) ? (u_end - u) : (p.nk - kc0);
-                for (int64_t kc = kc0; kc < kc0 + len; ++kc) {
+                // K order of a segment: upward -- except, with p.reverse_tail, a segment that does not start at K = 0
+                // (the tail of a tile whose head another CTA computes) runs downward from its end.  Every CTA starts
+                // with such a tail, so all of them then read the SAME chunks of the factor B at the same time (they all
+                // begin at the last chunk) and B is fetched from DRAM once instead of once per tile: with a stream-K
+                // split the K offsets of the CTAs are otherwise spread over the whole range, and a 64 MB factor
+                // (config 5, T half-step) does not survive in L2 next to the X stream.
+                const bool down = p.reverse_tail && kc0 != 0;
+                for (int64_t i = 0; i < len; ++i) {
+                    const int64_t kc = down ? (kc0 + len - 1 - i) : (kc0 + i);
                     mbar_wait(&empty[stage], phase ^ 1, err, 1);
                     mbar_expect_tx(&full[stage], (uint32_t)(a_stage + b_stage));
                     if (s < p.n_super_main)
@@ -345,6 +354,7 @@ struct Tf32Gemm {
     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
     int force_mt = 0;
     int flush = FLUSH;
+    int reverse_tail = 0;
     int* ctr = nullptr;
     size_t ctr_len = 0;
 };
@@ -377,6 +387,8 @@ Tf32Gemm* tf32_gemm_create(int sm_count, int nmax, std::string& err)
     if (ev && ev[0] == '1') g->dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     const char* mt = getenv("RRI_GEMM_MT");
     if (mt) g->force_mt = atoi(mt);
+    const char* rt = getenv("RRI_GEMM_REVERSE_TAIL");
+    if (rt) g->reverse_tail = atoi(rt);
     const char* fl = getenv("RRI_GEMM_FLUSH");       // 0 = never flush (one TMEM accumulation per segment)
     if (fl) g->flush = atoi(fl);
     return g;
@@ -430,6 +442,7 @@ static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     while (cols < p.nbuf * MT * NPAD) cols <<= 1;
     p.tmem_cols = cols;
     p.flush = g->flush > 0 ? g->flush : (1 << 30);
+    p.reverse_tail = g->reverse_tail;
     int64_t grid = p.units < g->sm_count ? p.units : g->sm_count;
     constexpr int EWQ = NPAD >= 128 ? 4 : 2;
     auto kern = tf32_gemm_kernel<MT, NPAD, EWQ>;
