@@ -354,7 +354,7 @@ struct Tf32Gemm {
     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
     int force_mt = 0;
     int flush = FLUSH;
-    int reverse_tail = 0;
+    int reverse_tail = -1;             // -1: automatic (on for N > 64), 0 / 1: forced by RRI_GEMM_REVERSE_TAIL
     int* ctr = nullptr;
     size_t ctr_len = 0;
 };
@@ -442,7 +442,10 @@ static int run_cfg(Tf32Gemm* g, const CUtensorMap& tmA, const CUtensorMap& tmB, 
     while (cols < p.nbuf * MT * NPAD) cols <<= 1;
     p.tmem_cols = cols;
     p.flush = g->flush > 0 ? g->flush : (1 << 30);
-    p.reverse_tail = g->reverse_tail;
+    // Measured (profiles/r02_gemm_reverse_tail_ab.txt): the shared B stream wins where B is half of A's traffic (k = 128:
+    // T half-step of a config-5 shard 1.91 -> 1.76 ms) and loses where it is a quarter (k = 64: 2.49 -> 2.71 ms; streaming
+    // all CTAs through the same columns at the same time costs more than the re-reads it saves).
+    p.reverse_tail = g->reverse_tail >= 0 ? g->reverse_tail : (NPAD >= 128 ? 1 : 0);
     int64_t grid = p.units < g->sm_count ? p.units : g->sm_count;
     constexpr int EWQ = NPAD >= 128 ? 4 : 2;
     auto kern = tf32_gemm_kernel<MT, NPAD, EWQ>;
