@@ -832,9 +832,10 @@ static int hals_W_half(rri_handle_t h, T* W, const T* Tk, int64_t ldtk, const rr
     }
     const int parts = h->math == RRI_MATH_TF32 ? 1 : h->splits_w;
     // the zero-column test of nmf.py:793 is over ALL rows: with row shards the sums are all-reduced once per call
+    // (the per-topic sums and the zero-topic flags are taken once per call from W' and T: hals_finish_sums)
     launch_update_rows<T>(W, n, k, (const T*)h->Cpart, parts, n * k, nullptr, (const T*)h->Hm, solve_args(p, false),
                           (T*)h->Wt, h->ldwt, (T*)h->colsum_part, h->flags, h->ub_blocks_w,
-                          ColsumOut{h->sums, k, h->world > 1 ? 0 : 2, h->counters + 0}, st);
+                          ColsumOut{nullptr, k, 0, h->counters + 0}, st);
     h->launches++;
     CKL();
     return 0;
@@ -885,15 +886,25 @@ static int hals_T_half(rri_handle_t h, T* W, T* Tm, const rri_params_t* p, cudaS
     }
     // Tt (d x k) is updated in place; its transpose is written straight into the caller's T (k x d)
     launch_update_rows<T>((T*)h->Tt, d, k, C, parts, d * k, nullptr, G, solve_args(p, true), Tm, d, (T*)h->colsum_part,
-                          h->flags, h->ub_blocks_t, ColsumOut{h->sums, 0, 1, h->counters + 2}, st);
+                          h->flags, h->ub_blocks_t, ColsumOut{nullptr, 0, 0, h->counters + 2}, st);
     h->launches++;
     CKL();
     return 0;
 }
 
-// once per call on row shards: the zero-column test of nmf.py:793 is over ALL rows
-static int hals_finish_sums(rri_handle_t h, cudaStream_t st)
+// Once per call: sum(T[t,:]) and sum(W[:,t]) (nmf.py:757, :793) with the zero-topic flags, from the rows of T and of
+// W' -- a topic that empties inside a call makes the next half-step's denominator zero and raises the unbounded flag
+// anyway, so nothing is lost by not looking after every half-step.  On row shards the test on W is over ALL rows: the
+// shard sums are all-reduced.  (T sums: the peer exchange finalises them itself.)
+template <typename T>
+static int hals_finish_sums(rri_handle_t h, const T* Tm, bool t_updated, cudaStream_t st)
 {
+    launch_rowsum_flag<T>((const T*)h->Wt, h->k, h->n, h->ldwt, h->sums, h->k, h->world > 1 ? 0 : 2, h->flags, st);
+    h->launches++;
+    if (t_updated && !(h->world > 1 && h->p2p)) {
+        launch_rowsum_flag<T>(Tm, h->k, h->d, h->d, h->sums, 0, 1, h->flags, st);
+        h->launches++;
+    }
     if (h->world <= 1) return 0;
     NCK(g_nccl.AllReduce(h->sums + h->k, h->sums + h->k, (size_t)h->k, 8, 0, h->comm, st));
     launch_flag_from_sums(h->sums, h->k, h->k, 2, h->flags, st);
@@ -1189,7 +1200,7 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
         h->launches++;
         for (int s = 0; s < n_sweeps; ++s)
             if (hals_W_half<T>(h, W, Tm, d, p, s == 0, st)) return 1;
-        return hals_finish_sums(h, st);
+        return n_sweeps > 0 ? hals_finish_sums<T>(h, Tm, false, st) : 0;
     }
     if (h->order == RRI_ORDER_HALS) {
         launch_transpose<T>(Tm, k, d, d, (T*)h->Tt, k, st);
@@ -1209,7 +1220,7 @@ static int sweeps_impl(rri_handle_t h, T* W, T* Tm, int n_sweeps, const rri_para
         if (px) CK(cudaMemcpy2DAsync(Tm, (size_t)d * sizeof(T), Tk, (size_t)ldtk * sizeof(T), (size_t)d * sizeof(T), (size_t)k,
                                      cudaMemcpyDeviceToDevice, st));
         h->c2_valid = n_sweeps > 0;            // Cpart = X T' for the T just written, Tt = its transpose
-        return hals_finish_sums(h, st);
+        return n_sweeps > 0 ? hals_finish_sums<T>(h, Tm, true, st) : 0;
     }
     if (rri_prologue<T>(h, W, 0, p, st)) return 1;
     for (int s = 0; s < n_sweeps; ++s)
