@@ -446,6 +446,102 @@ sp_pass_blocked_kernel(const int64_t* __restrict__ ptr2, const int32_t* __restri
     }
 }
 
+// Streamlined form of the blocked pass for 16-bit block-local indices.  Same entry -> lane mapping and the same order
+// of additions as sp_pass_blocked_kernel (bit-identical sums), but
+//   * a sub-segment is addressed with 32-bit offsets from three base pointers (no 64-bit compare per entry),
+//   * trips with all 32*U entries present run without any predicate,
+//   * the remainder issues only the slots the warp needs (warp-uniform tests) -- with U = 16 almost every sub-segment
+//     of a config-4 shaped problem (~330-390 entries) is ONE batch of loads with 11-13 slots in flight per lane.
+template <typename T, bool HASW, int U, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+sp_pass_stream_kernel(const int64_t* __restrict__ ptr2, const uint16_t* __restrict__ idx16, T* __restrict__ E,
+                      const T* __restrict__ wgt, const Quad<T>* __restrict__ Q, const T* __restrict__ own_po,
+                      const T* __restrict__ own_pn, const T* __restrict__ own_cur, T* __restrict__ own_save,
+                      T* __restrict__ numer_part, T* __restrict__ denom_part, int64_t nseg, int nblk, int nb,
+                      int64_t nother, int chunks)
+{
+    extern __shared__ __align__(16) unsigned char sp_smem[];
+    Quad<T>* __restrict__ qs = reinterpret_cast<Quad<T>*>(sp_smem);
+    const int b = (int)(blockIdx.x % (unsigned)nblk), c = (int)(blockIdx.x / (unsigned)nblk);
+    const int64_t base = (int64_t)b * nb;
+    const int cnt = (int)((nother - base) < (int64_t)nb ? (nother - base) : (int64_t)nb);
+    for (int i = threadIdx.x; i < cnt; i += THREADS) qs[i] = Q[base + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NWARPS = THREADS / 32;
+    int64_t s0, s1;
+    part_range(nseg, chunks, c, s0, s1);
+    const bool apply = own_po != nullptr;
+    const int64_t pstride = (int64_t)nblk + 1;
+    int64_t s = s0 + warp;
+    int64_t beg = 0, end = 0;
+    T opo = T(0), opn = T(0), oc = T(0);
+    if (s < s1) {
+        beg = ptr2[s * pstride + b]; end = ptr2[s * pstride + b + 1];
+        opo = apply ? own_po[s] : T(0); opn = apply ? own_pn[s] : T(0); oc = own_cur[s];
+    }
+    while (s < s1) {
+        const int64_t sn = s + NWARPS;
+        int64_t nbeg = 0, nend = 0;
+        T nopo = T(0), nopn = T(0), noc = T(0);
+        if (sn < s1) {
+            nbeg = ptr2[sn * pstride + b]; nend = ptr2[sn * pstride + b + 1];
+            nopo = apply ? own_po[sn] : T(0); nopn = apply ? own_pn[sn] : T(0); noc = own_cur[sn];
+        }
+        T num = T(0), den = T(0);
+        const int len = (int)(end - beg);
+        const uint16_t* __restrict__ ip = idx16 + beg + lane;
+        T* __restrict__ Ep = E + beg + lane;
+        const T* __restrict__ wp = HASW ? wgt + beg + lane : nullptr;
+        int i = 0;
+        for (; i + 32 * U <= len; i += 32 * U) {                 // full trips: no predicates
+            uint32_t q[U]; T ev[U]; T m[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                q[u] = ip[i + 32 * u];
+                ev[u] = Ep[i + 32 * u];
+                m[u] = HASW ? wp[i + 32 * u] : T(1);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const Quad<T> qq = qs[q[u]];
+                sp_entry<T, HASW>(ev[u], qq, m[u], opo, opn, oc, apply, Ep + i + 32 * u, num, den);
+            }
+        }
+        const int rem = len - i;                                  // < 32 * U entries left (warp-uniform)
+        if (rem > 0) {
+            const int lrem = rem - lane;                          // slot u holds an entry for this lane iff 32u < lrem
+            uint32_t q[U]; T ev[U]; T m[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                q[u] = 0; ev[u] = T(0); m[u] = T(1);
+                if (32 * u < rem) {                               // warp-uniform: slots beyond the remainder are skipped
+                    const bool ok = 32 * u < lrem;
+                    if (ok) {
+                        q[u] = ip[i + 32 * u];
+                        ev[u] = Ep[i + 32 * u];
+                        if (HASW) m[u] = wp[i + 32 * u];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (32 * u < lrem) {
+                    const Quad<T> qq = qs[q[u]];
+                    sp_entry<T, HASW>(ev[u], qq, m[u], opo, opn, oc, apply, Ep + i + 32 * u, num, den);
+                }
+        }
+        num = warp_sum(num);
+        den = warp_sum(den);
+        if (lane == 0) {
+            numer_part[(int64_t)b * nseg + s] = num;
+            denom_part[(int64_t)b * nseg + s] = den;
+            if (b == 0) own_save[s] = oc;
+        }
+        s = sn; beg = nbeg; end = nend; opo = nopo; opn = nopn; oc = noc;
+    }
+}
+
 // ptr2[s][b] = first entry of segment s whose index is >= b * nb   (b = 0..nblk)
 __global__ void sp_subptr_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nseg, int nblk,
                                  int nb, int64_t* __restrict__ ptr2)
@@ -525,6 +621,48 @@ int launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* 
             kern<<<(unsigned)(s.nblk * chunks), 512, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save,
                                                                 numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks);
             return s.nblk;
+        }
+        if constexpr (sizeof(T) == 4) {
+            // RRI_SP_VARIANT (A/B): 1 = 512 threads x 16 entries per lane and trip, 2 = 512 x 24, 3 = 768 x 12 -- fewer
+            // warps with more entries in flight each (most sub-segments then finish in one trip)
+            static const int variant = [] { const char* e = getenv("RRI_SP_VARIANT"); return e ? atoi(e) : 0; }();
+            if (variant >= 4 && variant <= 8 && s.idx16) {
+#define RRI_SP_S(UU, TH, MB)                                                                                          \
+                do {                                                                                                  \
+                    if (w) {                                                                                          \
+                        auto kv = sp_pass_stream_kernel<T, true, UU, TH, MB>;                                         \
+                        cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);            \
+                        kv<<<(unsigned)(s.nblk * chunks), TH, smem, st>>>(s.ptr2, s.idx16, E, w, Q, own_po, own_pn, own_cur,    \
+                                                                          own_save, numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks); \
+                    } else {                                                                                          \
+                        auto kv = sp_pass_stream_kernel<T, false, UU, TH, MB>;                                        \
+                        cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);            \
+                        kv<<<(unsigned)(s.nblk * chunks), TH, smem, st>>>(s.ptr2, s.idx16, E, w, Q, own_po, own_pn, own_cur,    \
+                                                                          own_save, numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks); \
+                    }                                                                                                 \
+                    return s.nblk;                                                                                    \
+                } while (0)
+                if (variant == 4) RRI_SP_S(8, 1024, 1);
+                if (variant == 5) RRI_SP_S(16, 1024, 1);
+                if (variant == 6) RRI_SP_S(16, 512, 1);
+                if (variant == 7) RRI_SP_S(12, 1024, 1);
+                RRI_SP_S(16, 768, 1);
+#undef RRI_SP_S
+            }
+            if (variant >= 1 && variant <= 3 && !w) {
+#define RRI_SP_V(UU, TH)                                                                                              \
+                do {                                                                                                  \
+                    auto kv = sp_pass_blocked_kernel<T, false, UU, TH, 1>;                                            \
+                    cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);                \
+                    kv<<<(unsigned)(s.nblk * chunks), TH, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur,  \
+                                                                      own_save, numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks); \
+                    return s.nblk;                                                                                    \
+                } while (0)
+                if (variant == 1) RRI_SP_V(16, 512);
+                if (variant == 2) RRI_SP_V(24, 512);
+                RRI_SP_V(12, 768);
+#undef RRI_SP_V
+            }
         }
         auto kern = w ? sp_pass_blocked_kernel<T, true, U, 1024, 1> : sp_pass_blocked_kernel<T, false, U, 1024, 1>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
