@@ -566,7 +566,7 @@ int sp_block_len(int elem_size, int64_t nother, int* nblk_out)
 {
     // RRI_SP_BLOCK_KB: shared-memory staging block (default 128 KB: one 1024-thread CTA per SM; <= 64 KB: two
     // 512-thread CTAs per SM, shorter sub-segments)
-    static const int kb = [] { const char* e = getenv("RRI_SP_BLOCK_KB"); const int v = e ? atoi(e) : 128; return v >= 8 && v <= 128 ? v : 128; }();
+    static const int kb = [] { const char* e = getenv("RRI_SP_BLOCK_KB"); const int v = e ? atoi(e) : 128; return v >= 8 && v <= 216 ? v : 128; }();
     const int64_t cap = ((int64_t)kb * 1024) / (4 * elem_size);
     const int64_t nblk = nother > 0 ? (nother + cap - 1) / cap : 1;
     int64_t nb = (nother + nblk - 1) / nblk;
@@ -623,49 +623,27 @@ int launch_sp_pass(const SpSide& s, const void* quad, const T* own_po, const T* 
             return s.nblk;
         }
         if constexpr (sizeof(T) == 4) {
-            // RRI_SP_VARIANT (A/B): 1 = 512 threads x 16 entries per lane and trip, 2 = 512 x 24, 3 = 768 x 12 -- fewer
-            // warps with more entries in flight each (most sub-segments then finish in one trip)
-            static const int variant = [] { const char* e = getenv("RRI_SP_VARIANT"); return e ? atoi(e) : 0; }();
-            if (variant >= 4 && variant <= 8 && s.idx16) {
-#define RRI_SP_S(UU, TH, MB)                                                                                          \
-                do {                                                                                                  \
-                    if (w) {                                                                                          \
-                        auto kv = sp_pass_stream_kernel<T, true, UU, TH, MB>;                                         \
-                        cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);            \
-                        kv<<<(unsigned)(s.nblk * chunks), TH, smem, st>>>(s.ptr2, s.idx16, E, w, Q, own_po, own_pn, own_cur,    \
-                                                                          own_save, numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks); \
-                    } else {                                                                                          \
-                        auto kv = sp_pass_stream_kernel<T, false, UU, TH, MB>;                                        \
-                        cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);            \
-                        kv<<<(unsigned)(s.nblk * chunks), TH, smem, st>>>(s.ptr2, s.idx16, E, w, Q, own_po, own_pn, own_cur,    \
-                                                                          own_save, numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks); \
-                    }                                                                                                 \
-                    return s.nblk;                                                                                    \
-                } while (0)
-                if (variant == 4) RRI_SP_S(8, 1024, 1);
-                if (variant == 5) RRI_SP_S(16, 1024, 1);
-                if (variant == 6) RRI_SP_S(16, 512, 1);
-                if (variant == 7) RRI_SP_S(12, 1024, 1);
-                RRI_SP_S(16, 768, 1);
-#undef RRI_SP_S
-            }
-            if (variant >= 1 && variant <= 3 && !w) {
-#define RRI_SP_V(UU, TH)                                                                                              \
-                do {                                                                                                  \
-                    auto kv = sp_pass_blocked_kernel<T, false, UU, TH, 1>;                                            \
-                    cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);                \
-                    kv<<<(unsigned)(s.nblk * chunks), TH, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur,  \
-                                                                      own_save, numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks); \
-                    return s.nblk;                                                                                    \
-                } while (0)
-                if (variant == 1) RRI_SP_V(16, 512);
-                if (variant == 2) RRI_SP_V(24, 512);
-                RRI_SP_V(12, 768);
-#undef RRI_SP_V
+            // fp32 with 16-bit block-local indices: the streamlined kernel, 16 entries per lane and batch where no
+            // weights are read (64 registers, no spills), 8 with weights.  RRI_SP_STREAM=0 selects the general kernel
+            // below (A/B in profiles/r02_sparse_shape_ab_call16.txt, r02_sparse_pass_experiments.txt).
+            static const bool stream = [] { const char* e = getenv("RRI_SP_STREAM"); return !(e && *e == '0'); }();
+            if (stream && s.idx16) {
+                if (w) {
+                    auto kv = sp_pass_stream_kernel<T, true, 8, 1024, 1>;
+                    if (smem > 48 * 1024) cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kv<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save,
+                                                                       numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks);
+                } else {
+                    auto kv = sp_pass_stream_kernel<T, false, 16, 1024, 1>;
+                    if (smem > 48 * 1024) cudaFuncSetAttribute(kv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kv<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save,
+                                                                       numer, denom, s.nseg, s.nblk, s.nb, s.nother, chunks);
+                }
+                return s.nblk;
             }
         }
         auto kern = w ? sp_pass_blocked_kernel<T, true, U, 1024, 1> : sp_pass_blocked_kernel<T, false, U, 1024, 1>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kern<<<(unsigned)(s.nblk * chunks), 1024, smem, st>>>(s.ptr2, s.idx, s.idx16, E, w, Q, own_po, own_pn, own_cur, own_save, numer,
                                                              denom, s.nseg, s.nblk, s.nb, s.nother, chunks);
         return s.nblk;

@@ -178,3 +178,23 @@ def test_sparse_residual_carried_across_sweeps(cuda_device):
     assert relfro(a['W'], o['W']) < 1e-9 and relfro(a['T'], o['T']) < 1e-9
     assert relfro(b['W'], o['W']) < 1e-9 and relfro(b['T'], o['T']) < 1e-9
     assert relfro(b['W'], a['W']) < 1e-11
+
+
+@pytest.mark.parametrize('weighted', [False, True])
+def test_sparse_fp32_long_factor_streamlined_pass(R, weighted):
+    """fp32 with a gathered factor longer than one 64 KB staging block (9000 rows -> two blocks of 4500 records on the
+    column side): the T-steps run through sp_pass_stream_kernel (16 entries per lane and batch; 8 with entry weights),
+    the W-steps through the two-CTA kernel.  Final relative error within 1e-4 of the fp64 oracle, factors within 1e-3."""
+    n, d, k = 9000, 160, 4
+    X, W0, T0, Mb = orc.synth(n, d, k, k, sigma=0.05, seed=33, mask_density=0.06)
+    kw = {}
+    M = Mb
+    if weighted:
+        M = Mb * (0.5 + np.random.RandomState(4).rand(n, d))
+        kw['W_mat'] = observed(M, Mb).astype(np.float32)
+    o = orc.nmf_oracle(X, k, W0, T0, max_iter=4, W_mat=M)
+    out = run(R, observed(X, Mb).astype(np.float32), k, W0.astype(np.float32), T0.astype(np.float32), max_iter=4, **kw)
+    re_o = orc.rel_error(X, o['W'], o['T'], Mb)
+    re_g = orc.rel_error(X, out['W'].astype(np.float64), out['T'].astype(np.float64), Mb)
+    assert abs(re_o - re_g) < 1e-4, (re_o, re_g)
+    assert relfro(out['W'], o['W']) < 1e-3 and relfro(out['T'], o['T']) < 1e-3

@@ -1,5 +1,5 @@
 """Timing of the observed-entries (sparse) WRRI path at config-4 shape, next to the dense masked path on the same
-data:  python tools/bench_sparse.py [rows] [order] [sweeps] [refresh_every] [--dense]
+data:  python tools/bench_sparse.py [rows] [order] [sweeps] [refresh_every] [--dense] [--pattern=S]
 Prints one JSON line per path; bytes/sweep is the algorithmic figure of DESIGN.md (2k passes of 10 B per entry:
 2 B block-local index + 4 B residual read + 4 B residual written)."""
 import json, os, sys, time
@@ -18,7 +18,16 @@ g = torch.Generator(device=dev); g.manual_seed(0)
 U = torch.rand(rows, k, generator=g, device=dev); V = torch.rand(k, d, generator=g, device=dev)
 X = U @ V
 X += 0.05 * X.mean() * torch.rand(rows, d, generator=g, device=dev)
-M = torch.rand(rows, d, generator=g, device=dev) < density
+pattern = [a for a in sys.argv[1:] if a.startswith('--pattern=')]
+if pattern:
+    # regular pattern (i + j) % S == 0: consecutive entries of a row / column are S apart, so the shared-memory gather
+    # of 8 consecutive lanes is conflict-free for odd S and an 8-way conflict for S % 8 == 0 (experiment)
+    S = int(pattern[0].split('=')[1])
+    ii = torch.arange(rows, device=dev).view(-1, 1); jj = torch.arange(d, device=dev).view(1, -1)
+    M = ((ii + jj) % S) == 0
+    del ii, jj
+else:
+    M = torch.rand(rows, d, generator=g, device=dev) < density
 W0 = torch.rand(rows, k, generator=g, device=dev); T0 = torch.rand(k, d, generator=g, device=dev)
 Xs = (X * M).to_sparse_csr()
 nnz = int(Xs.values().numel())
@@ -33,7 +42,7 @@ def timed(eng, label, extra):
     torch.cuda.synchronize()
     e0.record(); eng.sweeps(W, T, sweeps, p, want_flags=False); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / sweeps
-    out = {'path': label, 'order': order, 'refresh_every': refresh_every, 'rows': rows, 'd': d, 'k': k, 'nnz': nnz, 'ms_per_sweep': round(ms, 3),
+    out = {'path': label, 'pattern': (pattern[0] if pattern else 'random'), 'order': order, 'refresh_every': refresh_every, 'rows': rows, 'd': d, 'k': k, 'nnz': nnz, 'ms_per_sweep': round(ms, 3),
            'sweeps_per_s': round(1000.0 / ms, 2), 'rel_err': round(eng.rel_error(W, T), 5)}
     out.update(extra(ms))
     print(json.dumps(out), flush=True)
