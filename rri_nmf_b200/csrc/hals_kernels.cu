@@ -451,10 +451,10 @@ static void launch_update_rows_tpr(T* F, int64_t m, int k, const T* Cpart, int p
 
 // ------------------------------------------------------------------------------------------------
 // row update, register-resident (the default when the contraction comes as one slice and k is a multiple of the
-// 16-byte vector): only the Gram matrix sits in shared memory, so 3 (k = 128) to 8 blocks share an SM where the staged
+// 16-byte vector): only the Gram matrix sits in shared memory, so 2 (k = 128) to 8 blocks share an SM where the staged
 // variant above fits one or two (its two staged tiles cost 66 KB at KM = 64, 132 KB at KM = 128).  A thread loads its
 // own factor row into registers with 16-byte loads, reads the contraction entry of each step straight from global
-// memory (sequential per thread: L1 lines are reused), and writes the row and its transpose itself.  Same direct form
+// memory (16-byte loads, one group of 8 steps ahead), and writes the row and its transpose itself.  Same direct form
 // and the same order of operations as update_rows_tpr_kernel -- the results are bit-identical.  Column sums are
 // taken afterwards from the transposed copy (rowsum_flag_kernel).  Config-5 shard (125 000 rows, k = 128): W update
 // 0.73 -> 0.43 ms, T update 0.23 -> 0.13 ms (profiles/r02_update_rows_reg_ab.txt).
@@ -488,9 +488,36 @@ update_rows_reg_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
 #pragma unroll
             for (int v = 0; v < VN; ++v) f[VN * jv + v] = fv[v];
         }
-        const T* crow = C + row * k;
+        // the contraction entries of 8 steps come as 16-byte loads, requested one group of steps ahead (a scalar load
+        // per step leaves its line in L1 for the next 31 steps of the same thread -- with 16 warps per SM walking 32
+        // rows each the lines do not survive, and every step waits for L2)
+        const V* crowv = reinterpret_cast<const V*>(C + row * k);
+        constexpr int GV = 8 / VN;                                                  // vectors per group of 8 steps
+        T cn[8];
+#pragma unroll
+        for (int v = 0; v < GV; ++v) {
+            T cv[VN];
+#pragma unroll
+            for (int x = 0; x < VN; ++x) cv[x] = T(0);
+            if (VN * v < k) unpack(crowv[v], cv);
+#pragma unroll
+            for (int x = 0; x < VN; ++x) cn[VN * v + x] = cv[x];
+        }
 #pragma unroll 1
         for (int c = 0; c < (k + 7) / 8; ++c) {
+            T cc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cc[u] = cn[u];
+#pragma unroll
+            for (int v = 0; v < GV; ++v) {
+                const int jv = GV * (c + 1) + v;
+                if (VN * jv < k) {
+                    T cv[VN];
+                    unpack(crowv[jv], cv);
+#pragma unroll
+                    for (int x = 0; x < VN; ++x) cn[VN * v + x] = cv[x];
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int t = 8 * c + u;
@@ -509,7 +536,7 @@ update_rows_reg_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
                     for (int jj = 1; jj < KM / 8; ++jj) ft = (jj == c) ? f[8 * jj + u] : ft;
                     const T stt = Ss[t * KM + t];
                     const T dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) - ft * stt;
-                    const T x = solve_scalar_c<T>(crow[t] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
+                    const T x = solve_scalar_c<T>(cc[u] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
 #pragma unroll
                     for (int jj = 0; jj < KM / 8; ++jj) f[8 * jj + u] = (jj == c) ? x : f[8 * jj + u];
                 }
