@@ -469,9 +469,11 @@ int tf32_gemm_run(Tf32Gemm* g, const float* A, int64_t lda, const float* B, int6
     if (N > g->nmax && N > 32) { err = "N exceeds the rank this handle was created for"; return -1; }
     int mt = (M > BM) ? 2 : 1;
     if (npad == 256) mt = 1;                     // 128 accumulator registers per epilogue thread at most
-    // fewer 256-row super-tiles than CTAs (the T half-step: M = d): 128-row tiles split more evenly -- measured
-    // 6-20 us per launch at M = 20 000, N = 64 (profiles/r02_gemm_tile_height_ab.txt); no gain at N = 128
-    if (npad <= 64 && (M + 2 * BM - 1) / (2 * BM) < g->sm_count) mt = 1;
+    // fewer 256-row super-tiles than CTAs (the T half-step of a row shard: M = d) and a factor B small enough to stay
+    // in L2 while twice as many tiles re-read it: 128-row tiles split more evenly -- measured 6-7 us per launch at
+    // M = 20 000, N = 64, K = 25 000 / 50 000 (profiles/r02_gemm_tile_height_ab.txt).  At K = 200 000 (B = 51 MB) the
+    // doubled re-reads cost 0.16 ms, and N = 128 gains nothing.
+    if (npad <= 64 && (M + 2 * BM - 1) / (2 * BM) < g->sm_count && (int64_t)npad * K * 4 <= ((int64_t)16 << 20)) mt = 1;
     if (g->force_mt == 1 || (g->force_mt == 2 && npad < 256)) mt = g->force_mt;
     CUtensorMap tmA, tmB, tmA2;
     if (!encode_2d(g, &tmA, A, M, K, lda, mt * BM, err)) return -1;
