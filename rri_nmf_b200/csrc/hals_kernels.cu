@@ -561,14 +561,127 @@ update_rows_reg_kernel(T* __restrict__ F, int64_t m, int k, const T* __restrict_
     if (unb) atomicOr(flags, 4);
 }
 
+// fp32 form of update_rows_reg_kernel on packed arithmetic: the factor row lives in 64-bit register pairs and the
+// dot product of a step is 32 fma.rn.f32x2 (two IEEE fp32 FMAs per instruction, sm_100) instead of 64 FFMA.  Lane 0 / 1
+// of accumulator pair 0 are the chains acc[0] / acc[1] of the scalar kernel, pair 1 holds acc[2] / acc[3], and the
+// products enter in the same order: the results are bit-identical.
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ unsigned long long pack_f(float lo, float hi)
+{
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
+template <int KM>
+__global__ void __launch_bounds__(128)
+update_rows_reg_x2_kernel(float* __restrict__ F, int64_t m, int k, const float* __restrict__ C, const float* __restrict__ S,
+                          float reg_l1, float reg_l2, float eps, float ub, int has_ub, float* __restrict__ Ft, int64_t ldft,
+                          int* __restrict__ flags)
+{
+    using U64 = unsigned long long;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Ss = reinterpret_cast<float*>(smem_raw);           // [KM][KM], zero padded
+    const int tid = threadIdx.x;
+    for (int e = tid; e < KM * KM; e += 128) {
+        const int a = e / KM, b = e % KM;
+        Ss[e] = (a < k && b < k) ? S[a * k + b] : 0.f;
+    }
+    __syncthreads();
+    bool unb = false;
+    for (int64_t row = (int64_t)blockIdx.x * 128 + tid; row < m; row += (int64_t)gridDim.x * 128) {
+        U64 fp[KM / 2];                                       // fp[j] = (f[2j], f[2j+1])
+        const ulonglong2* frowv = reinterpret_cast<const ulonglong2*>(F + row * k);      // k % 4 == 0
+#pragma unroll
+        for (int jv = 0; jv < KM / 4; ++jv) {
+            ulonglong2 v = make_ulonglong2(0ull, 0ull);
+            if (4 * jv < k) v = frowv[jv];
+            fp[2 * jv] = v.x; fp[2 * jv + 1] = v.y;
+        }
+        const float4* crowv = reinterpret_cast<const float4*>(C + row * k);
+        float cn[8];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * v < k) cv = crowv[v];
+            cn[4 * v] = cv.x; cn[4 * v + 1] = cv.y; cn[4 * v + 2] = cv.z; cn[4 * v + 3] = cv.w;
+        }
+#pragma unroll 1
+        for (int c = 0; c < (k + 7) / 8; ++c) {
+            float cc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cc[u] = cn[u];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const int jv = 2 * (c + 1) + v;
+                if (4 * jv < k) {
+                    const float4 cv = crowv[jv];
+                    cn[4 * v] = cv.x; cn[4 * v + 1] = cv.y; cn[4 * v + 2] = cv.z; cn[4 * v + 3] = cv.w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = 8 * c + u;
+                if (t < k) {
+                    const ulonglong2* srow = reinterpret_cast<const ulonglong2*>(Ss + t * KM);
+                    U64 a01 = 0ull, a23 = 0ull;
+#pragma unroll
+                    for (int jv = 0; jv < KM / 4; ++jv) {
+                        const ulonglong2 sv = srow[jv];
+                        ffma2(a01, fp[2 * jv], sv.x);
+                        ffma2(a23, fp[2 * jv + 1], sv.y);
+                    }
+                    // f[8 jj + u] = half (u & 1) of pair 4 jj + u / 2
+                    U64 fpair = fp[u / 2];
+#pragma unroll
+                    for (int jj = 1; jj < KM / 8; ++jj) fpair = (jj == c) ? fp[4 * jj + u / 2] : fpair;
+                    const float ft = (u & 1) ? hi_f(fpair) : lo_f(fpair);
+                    const float stt = Ss[t * KM + t];
+                    const float dot = ((lo_f(a01) + hi_f(a01)) + (lo_f(a23) + hi_f(a23))) - ft * stt;
+                    const float x = solve_scalar_c<float>(cc[u] - dot - reg_l1, stt + reg_l2, eps, ub, has_ub != 0, unb);
+#pragma unroll
+                    for (int jj = 0; jj < KM / 8; ++jj) {
+                        const U64 old = fp[4 * jj + u / 2];
+                        const U64 upd = (u & 1) ? pack_f(lo_f(old), x) : pack_f(x, hi_f(old));
+                        fp[4 * jj + u / 2] = (jj == c) ? upd : old;
+                    }
+                }
+            }
+        }
+        ulonglong2* fout = reinterpret_cast<ulonglong2*>(F + row * k);
+#pragma unroll
+        for (int jv = 0; jv < KM / 4; ++jv)
+            if (4 * jv < k) fout[jv] = make_ulonglong2(fp[2 * jv], fp[2 * jv + 1]);
+        if (Ft) {
+#pragma unroll
+            for (int t = 0; t < KM; ++t)
+                if (t < k) Ft[(int64_t)t * ldft + row] = (t & 1) ? hi_f(fp[t / 2]) : lo_f(fp[t / 2]);
+        }
+    }
+    if (unb) atomicOr(flags, 4);
+}
+
 template <typename T, int KM>
 static void launch_update_rows_reg(T* F, int64_t m, int k, const T* C, const T* S, const SolveArgs& a, T* Ft, int64_t ldft,
                                    int* flags, const ColsumOut& co, cudaStream_t st)
 {
     const size_t smem = sizeof(T) * KM * KM;
+    const int64_t nb = (m + 127) / 128;
+    if constexpr (sizeof(T) == 4) {
+        static const bool x2 = [] { const char* e = getenv("RRI_UPDATE_X2"); return !(e && *e == '0'); }();
+        if (x2) {
+            auto kx = update_rows_reg_x2_kernel<KM>;
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kx<<<(unsigned)nb, 128, smem, st>>>(F, m, k, C, S, (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft, flags);
+            if (co.sums) launch_rowsum_flag<T>(Ft, k, m, ldft, co.sums, co.off, co.zero_flag, flags, st);
+            return;
+        }
+    }
     auto kern = update_rows_reg_kernel<T, KM>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int64_t nb = (m + 127) / 128;
     kern<<<(unsigned)nb, 128, smem, st>>>(F, m, k, C, S, (T)a.reg_l1, (T)a.reg_l2, (T)a.eps, (T)a.ub, a.has_ub, Ft, ldft, flags);
     if (co.sums) launch_rowsum_flag<T>(Ft, k, m, ldft, co.sums, co.off, co.zero_flag, flags, st);
 }
