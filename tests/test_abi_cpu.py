@@ -105,3 +105,23 @@ def test_estimator_surface():
         assert hasattr(tm, m)
     for m in ('fit', 'fit_from_Xtr', 'transform', 'predict', 'score', 'make_Xpred', 'sparsify', 'densify'):
         assert hasattr(rs, m)
+
+
+def test_documented_switches_exist_in_the_sources():
+    """DESIGN.md §9a lists the A/B environment switches of the library; every one of them must be read somewhere in
+    csrc/ or the Python package, and every switch the CUDA sources read must be listed there."""
+    design = open(os.path.join(ROOT, 'DESIGN.md')).read()
+    sec = design[design.index('## 9a.'):design.index('## 10.')]
+    documented = set(re.findall(r'`(RRI_[A-Z0-9_]+)', sec))
+    read = set()
+    pkg = os.path.join(ROOT, 'rri_nmf_b200')
+    for d, _, files in os.walk(pkg):
+        if os.path.basename(d) == 'build':
+            continue
+        for f in files:
+            if f.endswith(('.cu', '.cuh', '.h', '.py')):
+                src = open(os.path.join(d, f)).read()
+                read |= set(re.findall(r'getenv\("(RRI_[A-Z0-9_]+)"\)', src))
+                read |= set(re.findall(r"environ(?:\.get)?[\(\[]\s*'(RRI_[A-Z0-9_]+)'", src))
+    assert documented <= read, sorted(documented - read)
+    assert read <= documented, sorted(read - documented)
