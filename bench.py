@@ -575,7 +575,7 @@ def main_masked(args):
         eng = R.RRIEngine(Xs, k, order=order)
         math = 'ieee'
         alg_bytes = 10.0 * nnz                          # 2 B local index + 4 B residual read + 4 B residual written
-        kname = 'sp_pass_blocked_kernel (one half-step over the observed entries)'
+        kname = 'sp_pass_stream_kernel + solve (one T half-step of one topic over the observed entries)'
     else:
         nnz = int(M.sum())
         math = args.math or 'tf32'
